@@ -1,0 +1,193 @@
+// In-place shared-memory FFT building blocks (power-of-two lengths, radix 2/4/8/16 stages).
+//
+// Replaces the numpy.fft (pocketfft) calls behind the reference's PSF operator,
+// sgp.py:109-117 / 571-579:  real(ifftn(TF * fftn(x))).
+//
+// Layout.  A batch of independent 1-D transforms lives in one shared-memory workspace; transform f
+// starts at f*fstride complex elements and element i sits at fpad(i) = i + (i >> pad_shift)
+// (one padding slot every 2^pad_shift elements, pad_shift = log2(last radix)), which makes both the
+// strided first stages and the unit-stride last stage bank-conflict free for 16-byte elements.
+//
+// Forward = decimation in frequency, natural order in -> digit-reversed order out; inverse = the
+// exact adjoint stage sequence, digit-reversed in -> natural out.  The pointwise work between the
+// two (two-for-one untangle, PSF-spectrum multiply) addresses frequencies through pos_of_freq(),
+// so no reordering pass is ever executed.  Every stage task reads and writes the same R slots, so
+// one block barrier per stage is enough.
+#pragma once
+#include "bsgp_math.cuh"
+
+namespace bsgp {
+
+struct FftPlan {
+    int n;          // transform length (power of two, >= 4)
+    int log2n;
+    int nstages;
+    int log2r[6];   // log2 of the radix of each forward stage
+    int pad_shift;  // log2 of the last radix
+    int plen;       // padded length: n + (n >> pad_shift)
+};
+
+BSGP_DEV int fpad(int i, int ps) { return i + (i >> ps); }
+
+// position (unpadded) of frequency k after the forward stages
+BSGP_DEV int pos_of_freq(const FftPlan& pl, int k) {
+    int p = 0, lg = pl.log2n;
+    for (int s = 0; s < pl.nstages; ++s) {
+        lg -= pl.log2r[s];
+        p += (k & ((1 << pl.log2r[s]) - 1)) << lg;
+        k >>= pl.log2r[s];
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-resident DFTs.  X[q] = sum_r v[r] w^(q r), w = exp(-+2 pi i / R); result left in v[q].
+// ---------------------------------------------------------------------------------------------
+template <bool INV, typename T> BSGP_DEV void dft2(cplx<T>& a, cplx<T>& b) {
+    cplx<T> t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+template <bool INV, typename T> BSGP_DEV void dft4(cplx<T>& a0, cplx<T>& a1, cplx<T>& a2, cplx<T>& a3) {
+    cplx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = crot<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    a1 = cadd(t1, t3);
+    a3 = csub(t1, t3);
+}
+
+// multiply by exp(-+ 2 pi i m / 16) for the constants needed by the radix-8/16 kernels
+template <int M16, bool INV, typename T> BSGP_DEV cplx<T> mul_w16(cplx<T> a) {
+    const T c1 = (T)0.92387953251128673848, s1 = (T)0.38268343236508978178, c2 = (T)0.70710678118654752440;
+    // forward twiddle = (cr, -si); inverse = (cr, +si)
+    T cr, si;
+    if (M16 == 0) return a;
+    if (M16 == 4) return crot<INV>(a);
+    if (M16 == 1) { cr = c1; si = s1; }
+    else if (M16 == 2) { cr = c2; si = c2; }
+    else if (M16 == 3) { cr = s1; si = c1; }
+    else if (M16 == 6) { cr = -c2; si = c2; }
+    else /* 9 */ { cr = -c1; si = -s1; }
+    if (INV) return cmake<T>(a.re * cr - a.im * si, a.re * si + a.im * cr);
+    return cmake<T>(a.re * cr + a.im * si, a.im * cr - a.re * si);
+}
+
+template <bool INV, typename T> BSGP_DEV void dft8(cplx<T>* v) {
+    // even / odd radix-4 halves, then the W8^k combine
+    dft4<INV>(v[0], v[2], v[4], v[6]);
+    dft4<INV>(v[1], v[3], v[5], v[7]);
+    cplx<T> o0 = v[1], o1 = mul_w16<2, INV>(v[3]), o2 = mul_w16<4, INV>(v[5]), o3 = mul_w16<6, INV>(v[7]);
+    cplx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+template <bool INV, typename T> BSGP_DEV void dft16(cplx<T>* v) {
+    // n = 4 n1 + n2, k = k1 + 4 k2
+    dft4<INV>(v[0], v[4], v[8], v[12]);    // n2 = 0 -> Y[0][k1] in v[0], v[4], v[8], v[12]
+    dft4<INV>(v[1], v[5], v[9], v[13]);    // n2 = 1
+    dft4<INV>(v[2], v[6], v[10], v[14]);   // n2 = 2
+    dft4<INV>(v[3], v[7], v[11], v[15]);   // n2 = 3
+    // Y[n2][k1] sits in v[4 k1 + n2]; twiddle by W16^(n2 k1)
+    v[5] = mul_w16<1, INV>(v[5]);   v[6] = mul_w16<2, INV>(v[6]);   v[7] = mul_w16<3, INV>(v[7]);
+    v[9] = mul_w16<2, INV>(v[9]);   v[10] = mul_w16<4, INV>(v[10]); v[11] = mul_w16<6, INV>(v[11]);
+    v[13] = mul_w16<3, INV>(v[13]); v[14] = mul_w16<6, INV>(v[14]); v[15] = mul_w16<9, INV>(v[15]);
+    // outer transforms over n2 for each k1: outputs X[k1 + 4 k2] land in v[4 k1 + k2]
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+    dft4<INV>(v[4], v[5], v[6], v[7]);
+    dft4<INV>(v[8], v[9], v[10], v[11]);
+    dft4<INV>(v[12], v[13], v[14], v[15]);
+    // transpose the 4x4 register tile so that v[q] = X[q]
+    cplx<T> t;
+    t = v[1]; v[1] = v[4]; v[4] = t;
+    t = v[2]; v[2] = v[8]; v[8] = t;
+    t = v[3]; v[3] = v[12]; v[12] = t;
+    t = v[6]; v[6] = v[9]; v[9] = t;
+    t = v[7]; v[7] = v[13]; v[13] = t;
+    t = v[11]; v[11] = v[14]; v[14] = t;
+}
+
+template <int LOG2R, bool INV, typename T> BSGP_DEV void dft_r(cplx<T>* v) {
+    if (LOG2R == 1) dft2<INV>(v[0], v[1]);
+    else if (LOG2R == 2) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else if (LOG2R == 3) dft8<INV>(v);
+    else dft16<INV>(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one butterfly task of one stage: block length 2^lgL, radix 2^LOG2R, element j of block blk.
+// forward:  V = DFT_R(v);  out[q] = V[q] * W_L^(q j)
+// inverse:  V[q] = in[q] * conj(W_L^(q j));  out = IDFT_R(V)          (unnormalised)
+// tw[] holds W_n^k, k in [0, n); W_L^(q j) = tw[q j (n / L)].
+// ---------------------------------------------------------------------------------------------
+template <int LOG2R, bool INV, typename T>
+BSGP_DEV void stage_task(cplx<T>* a, int ps, int lgL, int blk, int j, const cplx<T>* tw, int lg_twstep) {
+    constexpr int R = 1 << LOG2R;
+    const int lgS = lgL - LOG2R;
+    const int p0 = (blk << lgL) + j;
+    cplx<T> v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = a[fpad(p0 + (r << lgS), ps)];
+    if (!INV) {
+        dft_r<LOG2R, false>(v);
+        if (lgS > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tw[(q * j) << lg_twstep]);
+        }
+    } else {
+        if (lgS > 0) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], tw[(q * j) << lg_twstep]);
+        }
+        dft_r<LOG2R, true>(v);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[fpad(p0 + (r << lgS), ps)] = v[r];
+}
+
+template <int LOG2R, bool INV, class Ctx, typename T>
+BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, int lgL, const cplx<T>* tw) {
+    const int lg_per = pl.log2n - LOG2R;          // butterflies per transform
+    const int lgS = lgL - LOG2R;
+    const int total = nfft << lg_per;
+    for (int t = ctx.tid; t < total; t += ctx.nt) {
+        const int f = t >> lg_per, u = t & ((1 << lg_per) - 1);
+        stage_task<LOG2R, INV>(ws + (size_t)f * fstride, pl.pad_shift, lgL, u >> lgS, u & ((1 << lgS) - 1), tw,
+                               pl.log2n - lgL);
+    }
+    ctx.sync();
+}
+
+template <bool INV, class Ctx, typename T>
+BSGP_DEV void dispatch_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, int lg_r, int lgL,
+                             const cplx<T>* tw) {
+    switch (lg_r) {
+        case 1: run_stage<1, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+        case 2: run_stage<2, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+        case 3: run_stage<3, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+        default: run_stage<4, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+    }
+}
+
+// nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout).  Ends with a barrier.
+template <bool INV, class Ctx, typename T>
+BSGP_DEV void fft_batch(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+    if (!INV) {
+        int lgL = pl.log2n;
+        for (int s = 0; s < pl.nstages; ++s) {
+            dispatch_stage<false>(ctx, ws, nfft, fstride, pl, pl.log2r[s], lgL, tw);
+            lgL -= pl.log2r[s];
+        }
+    } else {
+        int lgL = 0;
+        for (int s = pl.nstages - 1; s >= 0; --s) {
+            lgL += pl.log2r[s];
+            dispatch_stage<true>(ctx, ws, nfft, fstride, pl, pl.log2r[s], lgL, tw);
+        }
+    }
+}
+
+}  // namespace bsgp

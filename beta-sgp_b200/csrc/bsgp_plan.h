@@ -1,0 +1,88 @@
+// Host-side planning shared by libbsgp (bsgp_kernels.cu) and the test-only emulation
+// (tests/host_emul): FFT stage factorisation, twiddle tables, cluster / tile geometry.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <vector>
+
+#include "bsgp_conv.cuh"
+
+namespace bsgp {
+
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Stage radices: every stage has an in-block stride >= 8 (conflict-free 16-byte quarter-warp
+// access) except the last, whose radix (8 or 16) sets the padding period.
+inline bool make_fft_plan(int n, FftPlan* pl) {
+    static const int table[16][5] = {
+        {0}, {0}, {0},
+        {3, 0},            // 8
+        {4, 0},            // 16
+        {2, 3, 0},         // 32   = 4 x 8
+        {3, 3, 0},         // 64   = 8 x 8
+        {3, 4, 0},         // 128  = 8 x 16
+        {4, 4, 0},         // 256  = 16 x 16
+        {3, 3, 3, 0},      // 512
+        {3, 3, 4, 0},      // 1024
+        {3, 4, 4, 0},      // 2048
+        {4, 4, 4, 0},      // 4096
+        {3, 3, 3, 4, 0},   // 8192
+        {3, 3, 4, 4, 0},   // 16384
+        {3, 4, 4, 4, 0}};  // 32768
+    if (!is_pow2(n) || n < 8 || n > 32768) return false;
+    pl->n = n;
+    pl->log2n = ilog2(n);
+    int ns = 0;
+    for (int s = 0; s < 6; ++s) pl->log2r[s] = 0;
+    while (table[pl->log2n][ns] != 0) { pl->log2r[ns] = table[pl->log2n][ns]; ++ns; }
+    pl->nstages = ns;
+    pl->pad_shift = pl->log2r[ns - 1];
+    pl->plen = n + (n >> pl->pad_shift);
+    return true;
+}
+
+// W_n^k = exp(-2 pi i k / n), k in [0, n), computed in long double and rounded once.
+template <typename T> inline void make_twiddles(int n, std::vector<cplx<T>>& tw) {
+    tw.resize(n);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < n; ++k) {
+        // reduce to the first octant for accuracy
+        int kk = k % n;
+        long double ang = two_pi * (long double)kk / (long double)n;
+        tw[k].re = (T)cosl(ang);
+        tw[k].im = (T)(-sinl(ang));
+    }
+    // exact values on the axes
+    tw[0].re = 1; tw[0].im = 0;
+    if (n % 4 == 0) { tw[n / 4].re = 0; tw[n / 4].im = -1; tw[n / 2].re = -1; tw[n / 2].im = 0; tw[3 * n / 4].re = 0; tw[3 * n / 4].im = 1; }
+}
+
+// Geometry for a cluster of G CTAs and a shared-memory FFT workspace of at most ws_limit bytes.
+// Returns false if the shape cannot be handled.
+inline bool make_geom(int ny, int nx, int G, size_t elem_bytes /* sizeof(cplx<T>) */, size_t ws_limit, ConvGeom* g,
+                      size_t* ws_bytes) {
+    if (!is_pow2(ny) || !is_pow2(nx) || ny < 16 || nx < 16) return false;
+    if (!make_fft_plan(nx, &g->px) || !make_fft_plan(ny, &g->py)) return false;
+    g->ny = ny; g->nx = nx; g->hx = nx / 2;
+    g->lg_nx = ilog2(nx); g->lg_ny = ilog2(ny); g->lg_hx = g->lg_nx - 1;
+    g->G = G;
+    if (ny % (2 * G) != 0 || (nx / 2) % G != 0) return false;
+    g->rows_per_cta = ny / G;
+    g->cols_per_cta = g->hx / G;
+    g->rowstride = g->px.plen;
+    g->colstride = g->py.plen | 1;                   // odd: conflict-free transposing loads
+    int rtp = g->rows_per_cta / 2;
+    while (rtp > 1 && (size_t)rtp * g->rowstride * elem_bytes > ws_limit) rtp >>= 1;
+    int ct = g->cols_per_cta;
+    while (ct > 1 && (size_t)ct * g->colstride * elem_bytes > ws_limit) ct >>= 1;
+    if ((size_t)rtp * g->rowstride * elem_bytes > ws_limit || (size_t)ct * g->colstride * elem_bytes > ws_limit) return false;
+    g->row_tile_pairs = rtp;
+    g->col_tile = ct;
+    g->lg_col_tile = ilog2(ct);
+    const size_t a = (size_t)rtp * g->rowstride * elem_bytes, b = (size_t)ct * g->colstride * elem_bytes;
+    *ws_bytes = a > b ? a : b;
+    return true;
+}
+
+}  // namespace bsgp

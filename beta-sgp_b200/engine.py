@@ -1,0 +1,262 @@
+"""Batched front end of libbsgp: plans, buffers and the `solve_batch` call.
+
+Host arrays (numpy) go through the library's ``*_host`` entry points; CUDA tensors (torch, used
+only as device-memory handles) go through the asynchronous device entry points on torch's current
+stream.  Nothing here computes: all arithmetic of the restoration loop runs in the CUDA kernels
+of csrc/bsgp_kernels.cu, and there is no CPU fallback.
+
+Mirrors the call shape of the reference's batched callers, which loop over images one at a time:
+application_sgp_star_stamps.py:56-105 and application_sgp_subdivisions.py:83-107.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import BsgpError, DIV_BETA, DIV_KL, check, lib
+
+_NP = {"float64": np.float64, "float32": np.float32}
+_DT = {"float64": _capi.BSGP_F64, "float32": _capi.BSGP_F32}
+
+_SOLVER_KEYS = ("init_recon", "proj_type", "stop_criterion", "MAXIT", "gamma", "beta", "alpha", "alpha_min", "alpha_max",
+                "M_alpha", "tau", "M", "max_projs", "verbose", "ccd_sat_level", "scale_data", "errflag",
+                "tol_convergence", "adapt_beta", "lr", "lr_exp_param", "schedule_lr")
+
+
+class Plan:
+    """One bsgp_plan: (ny, nx, dtype, device) -> twiddles, per-cluster scratch, PSF spectra."""
+
+    def __init__(self, ny, nx, dtype="float64", device=0, cluster_size=0, threads=0):
+        self.ny, self.nx, self.dtype, self.device = int(ny), int(nx), str(dtype), int(device)
+        if self.dtype not in _DT:
+            raise ValueError("dtype must be 'float64' or 'float32'")
+        self._h = C.c_void_p()
+        check(lib().bsgp_plan_create(self.ny, self.nx, _DT[self.dtype], self.device, C.byref(self._h)))
+        if cluster_size or threads:
+            check(lib().bsgp_plan_configure(self._h, int(cluster_size), int(threads)))
+        self._psf_key = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self):
+        i = _capi.PlanInfo()
+        check(lib().bsgp_plan_get_info(self._h, C.byref(i)))
+        return {f: getattr(i, f) for f, _ in i._fields_}
+
+    def set_psf(self, psf):
+        """psf: numpy [ny,nx] / [n,ny,nx] or a CUDA tensor of the same shapes."""
+        if _is_tensor(psf):
+            t = psf.contiguous()
+            n = 1 if t.dim() == 2 else t.shape[0]
+            check(lib().bsgp_set_psf(self._h, t.data_ptr(), n, _stream_ptr()))
+            self._psf_keepalive = t
+            return n
+        a = np.ascontiguousarray(psf, dtype=_NP[self.dtype])
+        n = 1 if a.ndim == 2 else a.shape[0]
+        if a.shape[-2:] != (self.ny, self.nx):
+            raise ValueError(f"PSF shape {a.shape[-2:]} must equal the image shape {(self.ny, self.nx)} "
+                             "(the reference's numpy A/AT closure has the same requirement, sgp.py:108-120)")
+        check(lib().bsgp_set_psf_host(self._h, a.ctypes.data, n))
+        return n
+
+    def apply_psf(self, x, adjoint=False):
+        """A(x) / AT(x) for numpy [ny,nx] or [n,ny,nx] (sgp.py:111-120)."""
+        a = np.ascontiguousarray(x, dtype=_NP[self.dtype])
+        n = 1 if a.ndim == 2 else a.shape[0]
+        y = np.empty_like(a)
+        check(lib().bsgp_apply_psf_host(self._h, a.ctypes.data, y.ctypes.data, n, int(bool(adjoint))))
+        return y
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().bsgp_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_plans = {}
+
+
+def get_plan(ny, nx, dtype="float64", device=0, cluster_size=0, threads=0):
+    key = (int(ny), int(nx), str(dtype), int(device), int(cluster_size), int(threads))
+    p = _plans.get(key)
+    if p is None:
+        p = Plan(*key)
+        _plans[key] = p
+    return p
+
+
+def clear_plans():
+    for p in _plans.values():
+        p.close()
+    _plans.clear()
+
+
+def _is_tensor(a):
+    return type(a).__module__.startswith("torch") and hasattr(a, "data_ptr")
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class BatchResult:
+    x: object                 # [B,ny,nx] restored images
+    iters: object             # [B]
+    status: object            # [B] 0 = ok
+    discr: object             # [B,MAXIT+1]
+    times: object             # [B,MAXIT+1]
+    stop_value: object
+    err: object
+    beta_final: object
+    proj_evals: object        # [B] total projection evaluations
+    ls_trials: object         # [B] total line-search evaluations
+    scalars: object           # [B,8]
+    trace: dict | None = None
+
+
+def _params(divergence, kw, has_flux):
+    unknown = set(kw) - set(_SOLVER_KEYS)
+    if unknown:
+        raise TypeError(f"unexpected keyword argument(s): {sorted(unknown)}")
+    return _capi.make_params(DIV_KL if divergence == "kl" else DIV_BETA, has_flux=has_flux, **kw)
+
+
+def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=None, obj=None, dtype="float64",
+                device=0, trace=False, plan=None, psf_is_set=False, **kw):
+    """Restore a batch of independent images in one persistent kernel launch.
+
+    gn [B,ny,nx]; psf [ny,nx] (shared) or [B,ny,nx]; bkg scalar, [B] or [B,ny,nx]; flux None or [B];
+    betaParam scalar or [B].  Keyword arguments are those of sgp()/sgp_betaDiv() (sgp.py:41-47,
+    506-513).  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (asynchronous on the
+    current stream)."""
+    if divergence not in ("kl", "beta"):
+        raise ValueError("divergence must be 'kl' or 'beta'")
+    if _is_tensor(gn):
+        return _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw)
+    npdt = _NP[dtype]
+    gn = np.ascontiguousarray(gn, dtype=npdt)
+    if gn.ndim != 3:
+        raise ValueError("gn must be [batch, ny, nx]")
+    B, ny, nx = gn.shape
+    p = _params(divergence, kw, flux is not None)
+    plan = plan or get_plan(ny, nx, dtype, device)
+    if not psf_is_set:
+        n_psf = plan.set_psf(psf)
+        if n_psf not in (1, B):
+            raise ValueError("psf must be one image or one per batch entry")
+    bkg = np.asarray(bkg, dtype=npdt)
+    if bkg.ndim == 3:
+        bkg_img, bkg_a = 1, np.ascontiguousarray(bkg)
+        if bkg_a.shape != gn.shape:
+            raise ValueError("bkg image stack must have the shape of gn")
+    else:
+        bkg_img, bkg_a = 0, np.ascontiguousarray(np.broadcast_to(bkg.reshape(-1), (B,)).astype(npdt))
+    fl = None if flux is None else np.ascontiguousarray(np.broadcast_to(np.asarray(flux, dtype=np.float64).reshape(-1), (B,)))
+    b0 = np.ascontiguousarray(np.broadcast_to(np.asarray(betaParam, dtype=np.float64).reshape(-1), (B,)))
+    x0a = None if x0 is None else np.ascontiguousarray(x0, dtype=npdt)
+    obja = None if obj is None else np.ascontiguousarray(obj, dtype=npdt)
+    if p.init_recon == 1 and x0a is None:
+        raise ValueError("init_recon=1 needs x0 (the sgp()/sgp_betaDiv() wrappers draw it with seed 42)")
+    T = p.maxit + 1
+    out = dict(x=np.empty((B, ny, nx), npdt), iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32),
+               discr=np.zeros((B, T)), times=np.zeros((B, T)), stop_value=np.zeros((B, T)),
+               err=np.zeros((B, T + 1)) if p.errflag else None, beta_final=np.zeros(B), proj_evals=np.zeros(B, np.int32),
+               ls_trials=np.zeros(B, np.int32), scalars=np.zeros((B, _capi.NSCALARS)))
+    tr = None
+    if trace:
+        tr = dict(alpha=np.zeros((B, T)), lam=np.zeros((B, T)), beta=np.zeros((B, T)), trials=np.zeros((B, T), np.int32),
+                  evals=np.zeros((B, T), np.int32))
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data
+
+    ci = _capi.Inputs(ptr(gn), ptr(bkg_a), bkg_img, ptr(fl), ptr(b0), ptr(x0a), ptr(obja))
+    co = _capi.Outputs(ptr(out["x"]), ptr(out["iters"]), ptr(out["status"]), ptr(out["discr"]), ptr(out["times"]),
+                       ptr(out["stop_value"]), ptr(out["err"]), ptr(out["beta_final"]), ptr(out["proj_evals"]),
+                       ptr(out["ls_trials"]), ptr(out["scalars"]),
+                       ptr(tr["alpha"]) if tr else None, ptr(tr["lam"]) if tr else None, ptr(tr["beta"]) if tr else None,
+                       ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
+    check(lib().bsgp_solve_batch_host(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co)))
+    return BatchResult(trace=tr, **out)
+
+
+def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw):
+    import torch
+    if not gn.is_cuda:
+        raise BsgpError("tensor inputs must live on a CUDA device (there is no CPU path)")
+    dev = gn.device
+    dtype = {torch.float64: "float64", torch.float32: "float32"}[gn.dtype]
+    gn = gn.contiguous()
+    B, ny, nx = gn.shape
+    p = _params(divergence, kw, flux is not None)
+    plan = plan or get_plan(ny, nx, dtype, dev.index or 0)
+    with torch.cuda.device(dev):
+        if not psf_is_set:
+            n_psf = plan.set_psf(psf if _is_tensor(psf) else torch.as_tensor(np.ascontiguousarray(psf), dtype=gn.dtype, device=dev))
+            if n_psf not in (1, B):
+                raise ValueError("psf must be one image or one per batch entry")
+        if _is_tensor(bkg) and bkg.dim() == 3:
+            bkg_img, bkg_t = 1, bkg.contiguous()
+        else:
+            bkg_img = 0
+            bkg_t = (bkg if _is_tensor(bkg) else torch.as_tensor(np.asarray(bkg, dtype=np.float64), device=dev)).to(gn.dtype).reshape(-1).expand(B).contiguous()
+        f64 = dict(dtype=torch.float64, device=dev)
+        fl = None if flux is None else (flux if _is_tensor(flux) else torch.as_tensor(np.asarray(flux, dtype=np.float64), device=dev)).to(torch.float64).reshape(-1).expand(B).contiguous()
+        b0 = (betaParam if _is_tensor(betaParam) else torch.as_tensor(np.asarray(betaParam, dtype=np.float64), device=dev)).to(torch.float64).reshape(-1).expand(B).contiguous()
+        x0t = None if x0 is None else x0.contiguous()
+        objt = None if obj is None else obj.contiguous()
+        T = p.maxit + 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        out = dict(x=torch.empty_like(gn), iters=torch.zeros(B, **i32), status=torch.zeros(B, **i32),
+                   discr=torch.zeros(B, T, **f64), times=torch.zeros(B, T, **f64), stop_value=torch.zeros(B, T, **f64),
+                   err=torch.zeros(B, T + 1, **f64) if p.errflag else None, beta_final=torch.zeros(B, **f64),
+                   proj_evals=torch.zeros(B, **i32), ls_trials=torch.zeros(B, **i32),
+                   scalars=torch.zeros(B, _capi.NSCALARS, **f64))
+        tr = None
+        if trace:
+            tr = dict(alpha=torch.zeros(B, T, **f64), lam=torch.zeros(B, T, **f64), beta=torch.zeros(B, T, **f64),
+                      trials=torch.zeros(B, T, **i32), evals=torch.zeros(B, T, **i32))
+
+        def ptr(t):
+            return None if t is None else t.data_ptr()
+
+        ci = _capi.Inputs(ptr(gn), ptr(bkg_t), bkg_img, ptr(fl), ptr(b0), ptr(x0t), ptr(objt))
+        co = _capi.Outputs(ptr(out["x"]), ptr(out["iters"]), ptr(out["status"]), ptr(out["discr"]), ptr(out["times"]),
+                           ptr(out["stop_value"]), ptr(out["err"]), ptr(out["beta_final"]), ptr(out["proj_evals"]),
+                           ptr(out["ls_trials"]), ptr(out["scalars"]),
+                           ptr(tr["alpha"]) if tr else None, ptr(tr["lam"]) if tr else None, ptr(tr["beta"]) if tr else None,
+                           ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
+        check(lib().bsgp_solve_batch(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co), _stream_ptr()))
+        res = BatchResult(trace=tr, **out)
+        res._keepalive = (gn, bkg_t, fl, b0, x0t, objt)
+    return res
+
+
+def project_batch(b, c, dia, sat_cap=None, lambda_=0.0, dlambda_=1.0, tol_lam=1e-11, max_projs=1000, device=0):
+    """projectDF for a batch of problems: c, dia [B,n]; b [B] (flux_conserve_proj.py:7-144)."""
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    dia = np.ascontiguousarray(dia, dtype=np.float64)
+    if c.ndim == 1:
+        c, dia = c[None], dia[None]
+    B, n = c.shape
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64).reshape(-1), (B,)))
+    x = np.empty_like(c)
+    ev = np.zeros(B, np.int32)
+    st = np.zeros(B, np.int32)
+    cap = float("nan") if sat_cap is None else float(sat_cap)
+    check(lib().bsgp_project_df_host(b.ctypes.data, c.ctypes.data, dia.ctypes.data, n, B, cap, float(lambda_), float(dlambda_),
+                                     float(tol_lam), int(max_projs), x.ctypes.data, ev.ctypes.data, st.ctypes.data, int(device)))
+    return x, ev, st

@@ -80,6 +80,10 @@ def main():
              "alpha": np.array(o.trace.alpha), "lam": np.array(o.trace.lam),
              "beta_trace": np.array(o.trace.beta_param), "init_proj_evals": o.trace.init_proj_evals,
              "x_low": o.trace.x_low, "x_upp": o.trace.x_upp}
+        if "flux" in kw:
+            g["flux_in"] = float(kw["flux"])
+        if "betaParam" in kw:
+            g["beta0"] = float(kw["betaParam"])
         if div == "beta":
             m = re.search(r"final value\): (\S+)", out.getvalue())
             g["beta_final"] = float(m.group(1))

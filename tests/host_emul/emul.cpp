@@ -1,0 +1,163 @@
+// TEST-ONLY single-thread emulation of the device headers (compiled with g++ -DBSGP_HOST_EMUL).
+//
+// It lets the CPU test-suite check the index arithmetic of the FFT / convolution phases (including
+// the multi-CTA row/column partition, emulated rank by rank) and the solver's controller logic
+// against the oracle on machines without a GPU.  It is NOT part of the product: nothing under
+// beta-sgp_b200/ loads this library and libbsgp.so does not contain it.
+#define BSGP_HOST_EMUL 1
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../beta-sgp_b200/csrc/bsgp_plan.h"
+#include "../../beta-sgp_b200/csrc/bsgp_solver.cuh"
+
+using namespace bsgp;
+
+struct HostCtx {
+    int tid = 0, nt = 1, rank = 0, G = 1;
+    void sync() {}
+    void cluster_sync() {}
+    void allreduce_sum(double*, int) {}
+    void allreduce_min(double&) {}
+    void allreduce_max(double&) {}
+    double now() { return 0.0; }
+};
+
+template <typename T> struct HostPlan {
+    ConvGeom g;
+    size_t ws_bytes;
+    std::vector<cplx<T>> twx, twy, ws, spec, tf;
+    bool init(int ny, int nx, int G, size_t ws_limit) {
+        if (!make_geom(ny, nx, G, sizeof(cplx<T>), ws_limit, &g, &ws_bytes)) return false;
+        make_twiddles<T>(nx, twx);
+        make_twiddles<T>(ny, twy);
+        ws.assign(ws_bytes / sizeof(cplx<T>) + 16, cmake<T>(0, 0));
+        spec.assign((size_t)ny * g.hx, cmake<T>(0, 0));
+        tf.assign((size_t)(g.hx + 1) * ny, cmake<T>(0, 0));
+        return true;
+    }
+    void make_tf(const T* psf) {
+        const int ny = g.ny, nx = g.nx;
+        for (int phase = 0; phase < 2; ++phase)
+            for (int r = 0; r < g.G; ++r) {
+                HostCtx ctx; ctx.rank = r; ctx.G = g.G;
+                const int r0 = r * g.rows_per_cta;
+                auto prod = [&](int row, int c) -> T {
+                    return psf[(size_t)((r0 + row + ny / 2) & (ny - 1)) * nx + ((c + nx / 2) & (nx - 1))];
+                };
+                if (phase == 0) conv_rows_forward(ctx, g, ws.data(), twx.data(), spec.data(), prod);
+                else conv_cols(ctx, g, ws.data(), twy.data(), spec.data(), tf.data(), CONV_MAKE_TF);
+            }
+    }
+    void apply(const T* x, T* y, int adjoint) {
+        const int nx = g.nx;
+        for (int phase = 0; phase < 3; ++phase)
+            for (int r = 0; r < g.G; ++r) {
+                HostCtx ctx; ctx.rank = r; ctx.G = g.G;
+                const int r0 = r * g.rows_per_cta;
+                auto prod = [&](int row, int c) -> T { return x[(size_t)(r0 + row) * nx + c]; };
+                auto cons = [&](int row, int c, T v) { y[(size_t)(r0 + row) * nx + c] = v; };
+                if (phase == 0) conv_rows_forward(ctx, g, ws.data(), twx.data(), spec.data(), prod);
+                else if (phase == 1) conv_cols(ctx, g, ws.data(), twy.data(), spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
+                else conv_rows_inverse(ctx, g, ws.data(), twx.data(), spec.data(), cons);
+            }
+    }
+};
+
+extern "C" {
+
+// 1-D transform check: forward then (optionally) inverse of `nfft` rows of length n (complex interleaved)
+int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after) {
+    FftPlan pl;
+    if (!make_fft_plan(n, &pl)) return 1;
+    std::vector<cplx<double>> tw;
+    make_twiddles<double>(n, tw);
+    const int stride = pl.plen + 1;
+    std::vector<cplx<double>> ws((size_t)nfft * stride);
+    for (int f = 0; f < nfft; ++f)
+        for (int i = 0; i < n; ++i) ws[(size_t)f * stride + fpad(i, pl.pad_shift)] = cmake<double>(in[2 * ((size_t)f * n + i)], in[2 * ((size_t)f * n + i) + 1]);
+    HostCtx ctx;
+    fft_batch<false>(ctx, ws.data(), nfft, stride, pl, tw.data());
+    if (inverse_after) fft_batch<true>(ctx, ws.data(), nfft, stride, pl, tw.data());
+    for (int f = 0; f < nfft; ++f)
+        for (int k = 0; k < n; ++k) {
+            const int p = inverse_after ? k : pos_of_freq(pl, k);
+            const cplx<double> z = ws[(size_t)f * stride + fpad(p, pl.pad_shift)];
+            out[2 * ((size_t)f * n + k)] = z.re;
+            out[2 * ((size_t)f * n + k) + 1] = z.im;
+        }
+    return 0;
+}
+
+// circular PSF convolution of one image with the cluster partition emulated rank by rank
+int emul_conv(int ny, int nx, int G, long long ws_limit, const double* x, const double* psf, int adjoint, double* y) {
+    HostPlan<double> pl;
+    if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
+    pl.make_tf(psf);
+    pl.apply(x, y, adjoint);
+    return 0;
+}
+
+int emul_conv_f32(int ny, int nx, int G, long long ws_limit, const float* x, const float* psf, int adjoint, float* y) {
+    HostPlan<float> pl;
+    if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
+    pl.make_tf(psf);
+    pl.apply(x, y, adjoint);
+    return 0;
+}
+
+// full solver, one image, one emulated CTA
+int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, const double* psf, const double* bkg,
+               int bkg_is_image, const double* flux, const double* beta0, const double* x0, const double* obj,
+               double* x_out, int* iters, int* status, double* discr, double* stop_value, double* err, double* beta_final,
+               int* proj_evals, int* ls_trials, double* scalars, double* tr_alpha, double* tr_lambda, double* tr_beta,
+               int* tr_trials, int* tr_evals) {
+    HostPlan<double> pl;
+    if (!pl.init(ny, nx, 1, (size_t)1 << 30)) return 1;
+    pl.make_tf(psf);
+    const size_t npix = (size_t)ny * nx;
+    std::vector<double> work(NBUF * npix, 0.0), times(params->maxit + 1, 0.0);
+    double* buf[NBUF];
+    for (int b = 0; b < NBUF; ++b) buf[b] = work.data() + b * npix;
+    SolveArgs<double> a;
+    memset(&a, 0, sizeof(a));
+    a.p = *params; a.g = pl.g; a.batch = 1;
+    a.gn = gn; a.bkg = bkg; a.bkg_is_image = bkg_is_image; a.flux = flux; a.beta0 = beta0; a.x0 = x0; a.obj = obj;
+    a.twx = pl.twx.data(); a.twy = pl.twy.data(); a.tf = pl.tf.data(); a.n_psf = 1;
+    a.x_out = x_out; a.iters = iters; a.status = status; a.discr = discr; a.times = times.data();
+    a.stop_value = stop_value; a.err = err; a.beta_final = beta_final; a.proj_evals = proj_evals; a.ls_trials = ls_trials;
+    a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
+    a.tr_evals = tr_evals;
+    HostCtx ctx;
+    solve_image<double>(ctx, a, buf, pl.ws.data(), pl.spec.data(), pl.tf.data(), 0);
+    return 0;
+}
+
+// projectDF root-find with the reference's x = (c + lambda) / dia evaluation
+int emul_project(const double* c, const double* dia, int n, double b, double sat_cap, int has_cap, int max_projs,
+                 double* x, int* evals) {
+    auto point = [&](int i, double lam) {
+        double v = ndiv(nadd(c[i], lam), dia[i]);
+        v = (v <= 0.0) ? 0.0 : v;
+        if (has_cap) v = (v >= sat_cap) ? sat_cap : v;
+        return v;
+    };
+    auto eval = [&](double lam) -> double {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += point(i, lam);
+        return s - b;
+    };
+    ProjResult pr = flux_rootfind(eval, b, max_projs);
+    for (int i = 0; i < n; ++i) x[i] = point(i, pr.lambda);
+    *evals = pr.evals;
+    return pr.status;
+}
+
+}  // extern "C"
+
+extern "C" int emul_sizeof_params() { return (int)sizeof(bsgp_params); }
+extern "C" int emul_sizeof_inputs() { return (int)sizeof(bsgp_inputs); }
+extern "C" int emul_sizeof_outputs() { return (int)sizeof(bsgp_outputs); }
+extern "C" int emul_sizeof_plan_info() { return (int)sizeof(bsgp_plan_info); }

@@ -1,0 +1,136 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol of include/bsgp.h, the
+ctypes structs match the C structs, the product fails loudly without a device, and the device headers
+— compiled for the host as a one-thread emulation, tests/host_emul — produce the reference's numbers:
+FFT stages, the cluster-partitioned convolution, the projection root-find and the solver controller."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import emul_helper as eh
+from cases import CASES, STRICT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+capi = eh.capi
+P = C.POINTER(C.c_double)
+
+
+def test_library_exports_header_symbols():
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libbsgp.so not built (run __graft_entry__.build())")
+    hdr = open(os.path.join(ROOT, "include", "bsgp.h")).read()
+    declared = set(re.findall(r"\b(bsgp_[a-z_0-9]+)\s*\(", hdr))
+    L = capi.lib()
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/bsgp.h but not exported"
+    assert declared == set(capi.EXPORTED)
+    assert b"sm_100a" in L.bsgp_version()
+
+
+def test_ctypes_structs_match_c_layout():
+    L = eh.lib()
+    assert C.sizeof(capi.Params) == L.emul_sizeof_params()
+    assert C.sizeof(capi.Inputs) == L.emul_sizeof_inputs()
+    assert C.sizeof(capi.Outputs) == L.emul_sizeof_outputs()
+    assert C.sizeof(capi.PlanInfo) == L.emul_sizeof_plan_info()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product raises; it never computes on the host."""
+    if not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libbsgp.so not built")
+    if capi.lib().bsgp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    import beta_sgp_b200 as b
+    img = np.ones((32, 32))
+    with pytest.raises(RuntimeError, match="libbsgp error"):
+        b.sgp_betaDiv_batch(img[None], img / img.sum(), 0.1, MAXIT=2)
+    with pytest.raises(RuntimeError, match="libbsgp error"):
+        b.projectDF(np.float64(1.0), np.ones(8), np.ones(8), 1.0)
+    pkg = os.path.join(ROOT, "beta-sgp_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f"{f} imports the oracle"
+            assert "host_emul" not in src and "libbsgp_emul" not in src, f"{f} reaches the test-only emulation"
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 4096, 8192])
+def test_emulated_fft_stages(n):
+    L = eh.lib()
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(3, n)) + 1j * rng.normal(size=(3, n))
+    xin = np.ascontiguousarray(x).view(np.float64).copy()
+    for inverse_after in (0, 1):
+        out = np.zeros_like(xin)
+        assert L.emul_fft1d(n, 3, xin.ctypes.data_as(P), out.ctypes.data_as(P), inverse_after) == 0
+        got = out.view(np.complex128).reshape(3, n)
+        ref = np.fft.fft(x, axis=1) if not inverse_after else x * n
+        assert np.abs(got - ref).max() <= 2e-15 * np.abs(ref).max() * np.log2(n)
+
+
+@pytest.mark.parametrize("ny,nx,G,ws", [(32, 32, 1, 1 << 20), (32, 32, 2, 1 << 20), (64, 64, 4, 1 << 20), (256, 256, 8, 72 * 1024),
+                                        (256, 256, 16, 72 * 1024), (128, 512, 8, 40 * 1024), (512, 128, 2, 72 * 1024), (64, 32, 2, 4096)])
+def test_emulated_cluster_convolution(ny, nx, G, ws):
+    """real(ifftn(TF * fftn(x))) with TF = fftn(fftshift(psf)) or conj (sgp.py:109-117), rows/columns
+    partitioned over G emulated CTAs and tiled to the workspace limit."""
+    L = eh.lib()
+    L.emul_conv.argtypes = [C.c_int] * 3 + [C.c_longlong, P, P, C.c_int, P]
+    rng = np.random.default_rng(ny * 1000 + nx + G)
+    x = rng.normal(size=(ny, nx))
+    psf = rng.random((ny, nx))
+    psf /= psf.sum()
+    for adjoint in (0, 1):
+        y = np.zeros((ny, nx))
+        assert L.emul_conv(ny, nx, G, ws, x.ctypes.data_as(P), psf.ctypes.data_as(P), adjoint, y.ctypes.data_as(P)) == 0
+        tf = np.fft.fftn(np.fft.fftshift(psf))
+        ref = np.real(np.fft.ifftn((np.conj(tf) if adjoint else tf) * np.fft.fftn(x)))
+        assert np.abs(y - ref).max() <= 5e-15 * np.abs(ref).max()
+
+
+def test_emulated_projection_known_answers(golden):
+    for i in range(12):
+        k = f"proj{i:02d}"
+        sat = float(golden[k + "/sat"])
+        cap = None if np.isnan(sat) else sat / float(golden[k + "/scaling"]) - np.finfo(float).eps
+        x, evals, st = eh.project(golden[k + "/c"], golden[k + "/dia"], float(golden[k + "/b"]), cap)
+        assert st == 0
+        assert evals == int(golden[k + "/evals"])
+        np.testing.assert_allclose(x, golden[k + "/x"], rtol=1e-9, atol=1e-12 * np.abs(golden[k + "/x"]).max())
+
+
+EMUL_CASES = ["ngc_kl_27", "ngc_beta_p1_stop3", "ngc_kl_p1_stop2", "ngc_kl_stop2_quiet", "ngc_kl_stop4", "ngc_kl_init0",
+              "ngc_kl_init1_p1", "ngc_kl_noscale_flux", "ngc_kl_nonmonotone", "sat_kl_default_stop", "ngc_beta_adapt",
+              "ngc_beta_is", "ngc_beta_one", "ngc_beta_two", "stamp00", "stamp01", "stamp06", "stamp10", "tile00", "tile07"]
+
+
+@pytest.mark.parametrize("name", EMUL_CASES)
+def test_emulated_solver_matches_reference(name, get_case, golden):
+    """bsgp_solver.cuh run as one emulated CTA: identical iteration counts, projection-evaluation counts
+    and stopping decisions; objective trace and image within the north-star tolerances."""
+    gn, psf, bkg, div, kw = get_case(name)
+    r = eh.solve(gn, psf, bkg, divergence=div, **kw)
+    assert r["status"] == 0
+    assert r["iters"] == int(golden[name + "/iters"])
+    ref = golden[name + "/discr"]
+    assert np.abs(r["discr"] - ref).max() <= 1e-10 * np.abs(ref).max()
+    xs = golden[name + "/x_sub"]
+    assert np.abs(r["x"][::8, ::8] - xs).max() <= 1e-8 * np.abs(xs).max()
+    assert np.array_equal(r["evals"], golden[name + "/proj_evals"])
+    assert r["proj_evals"] == int(golden[name + "/proj_evals"].sum() + golden[name + "/init_proj_evals"])
+    n = r["iters"]
+    # every line search but the (discarded) last one takes the reference's number of trials
+    assert np.array_equal(r["trials"][:n - 1], golden[name + "/trials"][:n - 1])
+    # step lengths agree wherever the step was not a line-search escape (lam < 1e-12: sk, yk are rounding noise)
+    real = golden[name + "/lam"][:n - 1] > 1e-6
+    np.testing.assert_allclose(r["alpha"][:n - 1][real], golden[name + "/alpha"][:n - 1][real], rtol=1e-6)
+    if div == "beta":
+        assert r["beta_final"] == pytest.approx(float(golden[name + "/beta_final"]), rel=1e-9)
+
+
+def test_emulated_solver_flags_bad_flux(fixtures):
+    gn, psf = fixtures["stamp0/gn"], fixtures["stamp0/psf"]
+    r = eh.solve(gn, psf, np.float64(1e9), divergence="beta", proj_type=1, init_recon=2, stop_criterion=3, MAXIT=5)
+    assert r["status"] == capi.ST_BAD_FLUX and r["iters"] == 0
