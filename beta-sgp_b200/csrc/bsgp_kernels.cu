@@ -305,6 +305,10 @@ template <typename T> static const void* solve_kernel_ptr(int threads) {
 template <typename T> static const void* conv_kernel_ptr() { return (const void*)bsgp_conv_kernel<T>; }
 
 static int launch_clustered(const void* func, int grid, int block, size_t smem, int G, cudaStream_t st, void** args) {
+    // the attribute is per function, not per plan: plans of different shapes share the kernels, so (re)state
+    // the dynamic shared-memory limit this launch needs
+    CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (G > 8) CU(cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
