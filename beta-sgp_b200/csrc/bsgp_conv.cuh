@@ -21,6 +21,13 @@
 // Scaling: rows_forward stores 2*A[k]; the stored PSF spectrum carries 0.5/(nx*ny) (0.25/(nx*ny)
 // for the two packed columns, whose untangle doubles once more), all powers of two, so the result
 // equals numpy's normalised ifftn without a separate scaling pass.
+//
+// Memory-level parallelism.  Per-image state that is not resident in shared memory lives in L2
+// (~700 cycles away).  Every loop that touches it works on PAIRS of adjacent pixels (one 16-byte
+// load per array and pair) and is written in two phases over a small register tile: first all
+// loads of U steps (independent, issued back to back), then the arithmetic and the stores.
+// Producers / consumers follow the same protocol: `fetch(i)` only loads (i = even slab pixel index,
+// returns a small struct of V2 values), `eval` / `apply` compute, accumulate and store.
 #pragma once
 #include "bsgp_fft.cuh"
 
@@ -42,33 +49,96 @@ struct ConvGeom {
 
 enum ConvMode { CONV_TF = 0, CONV_CTF = 1, CONV_MAKE_TF = 2 };
 
-// prod(local_row, col) -> T  for local_row in [0, rows_per_cta)
-template <class Ctx, typename T, class Prod>
-BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>* twx, cplx<T>* spec, Prod& prod) {
+// the scalars of ConvGeom the row passes need, copied to registers once per pass (the geometry itself
+// lives in shared memory, where every store through another pointer would force a reload)
+struct RowGeom { int nx, hx, lg_nx, lg_hx, rows_per_cta, row_tile_pairs, rowstride, ps; };
+BSGP_DEV RowGeom row_geom(const ConvGeom& g) {
+    RowGeom r;
+    r.nx = g.nx; r.hx = g.hx; r.lg_nx = g.lg_nx; r.lg_hx = g.lg_hx; r.rows_per_cta = g.rows_per_cta;
+    r.row_tile_pairs = g.row_tile_pairs; r.rowstride = g.rowstride; r.ps = g.px.pad_shift;
+    return r;
+}
+
+// two adjacent pixels
+template <typename T> struct alignas(2 * sizeof(T)) V2 {
+    T x, y;
+};
+template <typename T> BSGP_DEV V2<T> mk2(T x, T y) { V2<T> r; r.x = x; r.y = y; return r; }
+template <typename T> BSGP_DEV V2<T> ld2(const T* p, int i) { return *reinterpret_cast<const V2<T>*>(p + i); }
+template <typename T> BSGP_DEV void st2(T* p, int i, V2<T> v) { *reinterpret_cast<V2<T>*>(p + i) = v; }
+
+// small register tiles returned by the fetch phase of the batched loops
+template <typename T> struct In1 { V2<T> a; };
+template <typename T> struct In2 { V2<T> a, b; };
+template <typename T> struct In3 { V2<T> a, b, c; };
+template <typename T> struct In4 { V2<T> a, b, c, d; };
+template <typename T> struct In5 { V2<T> a, b, c, d, e; };
+
+// ppx[k] = padded workspace position of frequency k after the forward row stages (a shared-memory table;
+// evaluating pos_of_freq per element costs as many instructions as the butterflies themselves).
+template <class Ctx> BSGP_DEV void fill_pos_table(Ctx& ctx, const FftPlan& pl, unsigned short* tab) {
+    for (int k = ctx.tid; k < pl.n; k += ctx.nt) tab[k] = (unsigned short)fpad(pos_of_freq(pl, k), pl.pad_shift);
+}
+
+// Producer: In fetch(i); V2 eval(i, In) for the slab pixel pair (i, i + 1), i = local_row * nx + col.
+template <int U, class Ctx, typename T, class Fetch, class Eval>
+BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned ppx_off, cplx<T>* spec, Fetch& fetch, Eval& eval) {
+    cplx<T>* ws = smem_at<cplx<T>>(ws_off);
+    const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
+    const RowGeom g = row_geom(gg);                          // scalars in registers; the FFT plan stays where it is
+    const FftPlan& px = gg.px;
     const int r0 = ctx.rank * g.rows_per_cta;
-    const int ps = g.px.pad_shift;
+    const int ps = g.ps;
     const int ntiles = (g.rows_per_cta >> 1) / g.row_tile_pairs;
     for (int tile = 0; tile < ntiles; ++tile) {
         const int pair0 = tile * g.row_tile_pairs;
-        for (int e = ctx.tid; e < (g.row_tile_pairs << g.lg_nx); e += ctx.nt) {
-            const int p = e >> g.lg_nx, c = e & (g.nx - 1);
-            const int row = 2 * (pair0 + p);
-            const T v0 = prod(row, c);
-            const T v1 = prod(row + 1, c);
-            ws[(size_t)p * g.rowstride + fpad(c, ps)] = cmake<T>(v0, v1);
+        const int total = g.row_tile_pairs << g.lg_hx;      // steps: one row pair x one column pair
+        // full batches without guards (a guarded assignment would push the register tile into local memory)
+        int e0 = ctx.tid;
+        for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+            decltype(fetch(0)) in0[U], in1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * ctx.nt;
+                const int i0 = ((2 * (pair0 + (e >> g.lg_hx))) << g.lg_nx) + 2 * (e & (g.hx - 1));
+                in0[u] = fetch(i0);
+                in1[u] = fetch(i0 + g.nx);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * ctx.nt;
+                const int p = e >> g.lg_hx, c = 2 * (e & (g.hx - 1));
+                const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
+                const V2<T> v0 = eval(i0, in0[u]);
+                const V2<T> v1 = eval(i0 + g.nx, in1[u]);
+                cplx<T>* row = ws + p * g.rowstride;
+                row[fpad(c, ps)] = cmake<T>(v0.x, v1.x);
+                row[fpad(c + 1, ps)] = cmake<T>(v0.y, v1.y);
+            }
+        }
+        for (; e0 < total; e0 += ctx.nt) {
+            const int p = e0 >> g.lg_hx, c = 2 * (e0 & (g.hx - 1));
+            const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
+            const auto a0 = fetch(i0);
+            const auto a1 = fetch(i0 + g.nx);
+            const V2<T> v0 = eval(i0, a0);
+            const V2<T> v1 = eval(i0 + g.nx, a1);
+            cplx<T>* row = ws + p * g.rowstride;
+            row[fpad(c, ps)] = cmake<T>(v0.x, v1.x);
+            row[fpad(c + 1, ps)] = cmake<T>(v0.y, v1.y);
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws, g.row_tile_pairs, g.rowstride, g.px, twx);
-        for (int e = ctx.tid; e < (g.row_tile_pairs << g.lg_hx); e += ctx.nt) {
+        fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx);
+        for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int p = e >> g.lg_hx, k = e & (g.hx - 1);
-            const cplx<T>* a = ws + (size_t)p * g.rowstride;
+            const cplx<T>* a = ws + p * g.rowstride;
             cplx<T> A, B;
             if (k == 0) {
-                const cplx<T> z0 = a[fpad(pos_of_freq(g.px, 0), ps)], zh = a[fpad(pos_of_freq(g.px, g.hx), ps)];
+                const cplx<T> z0 = a[ppx[0]], zh = a[ppx[g.hx]];
                 A = cmake<T>(z0.re + z0.re, zh.re + zh.re);
                 B = cmake<T>(z0.im + z0.im, zh.im + zh.im);
             } else {
-                const cplx<T> zk = a[fpad(pos_of_freq(g.px, k), ps)], zm = a[fpad(pos_of_freq(g.px, g.nx - k), ps)];
+                const cplx<T> zk = a[ppx[k]], zm = a[ppx[g.nx - k]];
                 A = cmake<T>(zk.re + zm.re, zk.im - zm.im);
                 B = cmake<T>(zk.im + zm.im, zm.re - zk.re);
             }
@@ -81,33 +151,55 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const 
 }
 
 // tf: [hx + 1][ny] complex in column-workspace position order (written by CONV_MAKE_TF);
-// row 0 = kx 0, rows 1..hx-1 = kx, row hx = kx nx/2.
+// row 0 = kx 0, rows 1..hx-1 = kx, row hx = kx nx/2.  Not inlined: it does not depend on the
+// producer / consumer, so all convolutions of the solver share one copy of the code.
 template <class Ctx, typename T>
-BSGP_DEV void conv_cols(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>* twy, cplx<T>* spec, cplx<T>* tf, int mode) {
+BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, cplx<T>* spec, cplx<T>* tf, int mode) {
+    cplx<T>* ws = smem_at<cplx<T>>(ws_off);
+    constexpr int U = 8;
+    struct { int ny, nx, hx, lg_ny, lg_col_tile, col_tile, colstride, cols_per_cta; } g;      // register copies
+    g.ny = gp->ny; g.nx = gp->nx; g.hx = gp->hx; g.lg_ny = gp->lg_ny; g.lg_col_tile = gp->lg_col_tile; g.col_tile = gp->col_tile;
+    g.colstride = gp->colstride; g.cols_per_cta = gp->cols_per_cta;
+    const FftPlan& py = gp->py;
     const int c0 = ctx.rank * g.cols_per_cta;
-    const int ps = g.py.pad_shift;
+    const int ps = gp->py.pad_shift;
     const int ntiles = g.cols_per_cta / g.col_tile;
     const int ct = g.col_tile;
     for (int tile = 0; tile < ntiles; ++tile) {
         const int cc0 = c0 + tile * ct;
-        for (int e = ctx.tid; e < (g.ny << g.lg_col_tile); e += ctx.nt) {
-            const int row = e >> g.lg_col_tile, cl = e & (ct - 1);
-            ws[(size_t)cl * g.colstride + fpad(row, ps)] = spec[(size_t)row * g.hx + cc0 + cl];
+        const int total = g.ny << g.lg_col_tile;
+        {
+            int e0 = ctx.tid;
+            for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+                cplx<T> v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    v[u] = spec[(size_t)(e >> g.lg_col_tile) * g.hx + cc0 + (e & (ct - 1))];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    ws[(e & (ct - 1)) * g.colstride + fpad(e >> g.lg_col_tile, ps)] = v[u];
+                }
+            }
+            for (; e0 < total; e0 += ctx.nt)
+                ws[(e0 & (ct - 1)) * g.colstride + fpad(e0 >> g.lg_col_tile, ps)] = spec[(size_t)(e0 >> g.lg_col_tile) * g.hx + cc0 + (e0 & (ct - 1))];
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws, ct, g.colstride, g.py, twy);
+        fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy);
         if (mode == CONV_MAKE_TF) {
             // column FFT of 2*A holds 2*TF; store TF * 0.5/(nx ny)
             const T sc = (T)0.25 / ((T)g.nx * (T)g.ny);
             for (int e = ctx.tid; e < (ct << g.lg_ny); e += ctx.nt) {
                 const int cl = e >> g.lg_ny, p = e & (g.ny - 1);
                 if (cc0 + cl == 0) continue;
-                tf[(size_t)(cc0 + cl) * g.ny + p] = cscale(ws[(size_t)cl * g.colstride + fpad(p, ps)], sc);
+                tf[(size_t)(cc0 + cl) * g.ny + p] = cscale(ws[cl * g.colstride + fpad(p, ps)], sc);
             }
             if (cc0 == 0) {
                 const T sp = (T)0.0625 / ((T)g.nx * (T)g.ny);   // (C0 = 4 TF0) * 0.25/(nx ny)
                 for (int ky = ctx.tid; ky <= (g.ny >> 1); ky += ctx.nt) {
-                    const int pa = pos_of_freq(g.py, ky), pb = pos_of_freq(g.py, (g.ny - ky) & (g.ny - 1));
+                    const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, (g.ny - ky) & (g.ny - 1));
                     const cplx<T> za = ws[fpad(pa, ps)], zb = ws[fpad(pb, ps)];
                     const cplx<T> c0v = cmake<T>(za.re + zb.re, za.im - zb.im);          // za + conj(zb)
                     const cplx<T> chv = cmake<T>(za.im + zb.im, zb.re - za.re);          // -i (za - conj(zb))
@@ -120,20 +212,34 @@ BSGP_DEV void conv_cols(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>*
             ctx.sync();
             continue;
         }
-        for (int e = ctx.tid; e < (ct << g.lg_ny); e += ctx.nt) {
-            const int cl = e >> g.lg_ny, p = e & (g.ny - 1);
-            if (cc0 + cl == 0) continue;
-            cplx<T>* z = ws + (size_t)cl * g.colstride + fpad(p, ps);
-            const cplx<T> t = tf[(size_t)(cc0 + cl) * g.ny + p];
-            *z = (mode == CONV_TF) ? cmul(*z, t) : cmulc(*z, t);
+        const int mtotal = ct << g.lg_ny;
+        {
+            auto mul_one = [&](int e, const cplx<T>& t) {
+                if (cc0 + (e >> g.lg_ny) != 0) {
+                    cplx<T>* z = ws + (e >> g.lg_ny) * g.colstride + fpad(e & (g.ny - 1), ps);
+                    *z = (mode == CONV_TF) ? cmul(*z, t) : cmulc(*z, t);
+                }
+            };
+            int e0 = ctx.tid;
+            for (; e0 + (U - 1) * ctx.nt < mtotal; e0 += ctx.nt * U) {
+                cplx<T> t[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    t[u] = tf[(size_t)(cc0 + (e >> g.lg_ny)) * g.ny + (e & (g.ny - 1))];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) mul_one(e0 + u * ctx.nt, t[u]);
+            }
+            for (; e0 < mtotal; e0 += ctx.nt) mul_one(e0, tf[(size_t)(cc0 + (e0 >> g.lg_ny)) * g.ny + (e0 & (g.ny - 1))]);
         }
         if (cc0 == 0) {
             for (int ky = ctx.tid; ky <= (g.ny >> 1); ky += ctx.nt) {
-                const int pa = pos_of_freq(g.py, ky), pb = pos_of_freq(g.py, (g.ny - ky) & (g.ny - 1));
+                const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, (g.ny - ky) & (g.ny - 1));
+                cplx<T> t0a = tf[pa], tha = tf[(size_t)g.hx * g.ny + pa], t0b = tf[pb], thb = tf[(size_t)g.hx * g.ny + pb];
                 const cplx<T> za = ws[fpad(pa, ps)], zb = ws[fpad(pb, ps)];
                 const cplx<T> c0a = cmake<T>(za.re + zb.re, za.im - zb.im);
                 const cplx<T> cha = cmake<T>(za.im + zb.im, zb.re - za.re);
-                cplx<T> t0a = tf[pa], tha = tf[(size_t)g.hx * g.ny + pa], t0b = tf[pb], thb = tf[(size_t)g.hx * g.ny + pb];
                 if (mode == CONV_CTF) { t0a = cconj(t0a); tha = cconj(tha); t0b = cconj(t0b); thb = cconj(thb); }
                 const cplx<T> ya0 = cmul(t0a, c0a), yah = cmul(tha, cha);
                 const cplx<T> yb0 = cmul(t0b, cconj(c0a)), ybh = cmul(thb, cconj(cha));
@@ -143,62 +249,114 @@ BSGP_DEV void conv_cols(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>*
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws, ct, g.colstride, g.py, twy);
-        for (int e = ctx.tid; e < (g.ny << g.lg_col_tile); e += ctx.nt) {
+        fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy);
+        for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int row = e >> g.lg_col_tile, cl = e & (ct - 1);
-            spec[(size_t)row * g.hx + cc0 + cl] = ws[(size_t)cl * g.colstride + fpad(row, ps)];
+            spec[(size_t)row * g.hx + cc0 + cl] = ws[cl * g.colstride + fpad(row, ps)];
         }
         ctx.sync();
     }
 }
 
-// cons(local_row, col, value)
-template <class Ctx, typename T, class Cons>
-BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>* twx, const cplx<T>* spec, Cons& cons) {
+// Consumer: In fetch(i); void apply(i, In, V2 value) for the slab pixel pair (i, i + 1).
+template <int U, class Ctx, typename T, class Fetch, class Apply>
+BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
+    cplx<T>* ws = smem_at<cplx<T>>(ws_off);
+    const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
+    constexpr int UL = 4;
+    const RowGeom g = row_geom(gg);
+    const FftPlan& px = gg.px;
     const int r0 = ctx.rank * g.rows_per_cta;
-    const int ps = g.px.pad_shift;
+    const int ps = g.ps;
     const int ntiles = (g.rows_per_cta >> 1) / g.row_tile_pairs;
     for (int tile = 0; tile < ntiles; ++tile) {
         const int pair0 = tile * g.row_tile_pairs;
-        for (int e = ctx.tid; e < (g.row_tile_pairs << g.lg_hx); e += ctx.nt) {
-            const int p = e >> g.lg_hx, k = e & (g.hx - 1);
-            cplx<T>* a = ws + (size_t)p * g.rowstride;
-            const size_t row = (size_t)(r0 + 2 * (pair0 + p));
-            const cplx<T> A = spec[row * g.hx + k], B = spec[(row + 1) * g.hx + k];
-            if (k == 0) {
-                a[fpad(pos_of_freq(g.px, 0), ps)] = cmake<T>(A.re, B.re);
-                a[fpad(pos_of_freq(g.px, g.hx), ps)] = cmake<T>(A.im, B.im);
-            } else {
-                a[fpad(pos_of_freq(g.px, k), ps)] = cmake<T>(A.re - B.im, A.im + B.re);
-                a[fpad(pos_of_freq(g.px, g.nx - k), ps)] = cmake<T>(A.re + B.im, B.re - A.im);
+        const int total = g.row_tile_pairs << g.lg_hx;
+        {
+            auto tangle = [&](int e, const cplx<T>& A, const cplx<T>& B) {
+                const int k = e & (g.hx - 1);
+                cplx<T>* a = ws + (e >> g.lg_hx) * g.rowstride;
+                if (k == 0) {
+                    a[ppx[0]] = cmake<T>(A.re, B.re);
+                    a[ppx[g.hx]] = cmake<T>(A.im, B.im);
+                } else {
+                    a[ppx[k]] = cmake<T>(A.re - B.im, A.im + B.re);
+                    a[ppx[g.nx - k]] = cmake<T>(A.re + B.im, B.re - A.im);
+                }
+            };
+            int e0 = ctx.tid;
+            for (; e0 + (UL - 1) * ctx.nt < total; e0 += ctx.nt * UL) {
+                cplx<T> A[UL], B[UL];
+#pragma unroll
+                for (int u = 0; u < UL; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    const size_t row = (size_t)(r0 + 2 * (pair0 + (e >> g.lg_hx)));
+                    A[u] = spec[row * g.hx + (e & (g.hx - 1))];
+                    B[u] = spec[(row + 1) * g.hx + (e & (g.hx - 1))];
+                }
+#pragma unroll
+                for (int u = 0; u < UL; ++u) tangle(e0 + u * ctx.nt, A[u], B[u]);
+            }
+            for (; e0 < total; e0 += ctx.nt) {
+                const size_t row = (size_t)(r0 + 2 * (pair0 + (e0 >> g.lg_hx)));
+                tangle(e0, spec[row * g.hx + (e0 & (g.hx - 1))], spec[(row + 1) * g.hx + (e0 & (g.hx - 1))]);
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws, g.row_tile_pairs, g.rowstride, g.px, twx);
-        for (int e = ctx.tid; e < (g.row_tile_pairs << g.lg_nx); e += ctx.nt) {
-            const int p = e >> g.lg_nx, c = e & (g.nx - 1);
-            const cplx<T> z = ws[(size_t)p * g.rowstride + fpad(c, ps)];
-            const int row = 2 * (pair0 + p);
-            cons(row, c, z.re);
-            cons(row + 1, c, z.im);
+        fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx);
+        {
+            int e0 = ctx.tid;
+            for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+                decltype(fetch(0)) in0[U], in1[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    const int i0 = ((2 * (pair0 + (e >> g.lg_hx))) << g.lg_nx) + 2 * (e & (g.hx - 1));
+                    in0[u] = fetch(i0);
+                    in1[u] = fetch(i0 + g.nx);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * ctx.nt;
+                    const int p = e >> g.lg_hx, c = 2 * (e & (g.hx - 1));
+                    const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
+                    const cplx<T>* row = ws + p * g.rowstride;
+                    const cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                    apply(i0, in0[u], mk2<T>(z0.re, z1.re));
+                    apply(i0 + g.nx, in1[u], mk2<T>(z0.im, z1.im));
+                }
+            }
+            for (; e0 < total; e0 += ctx.nt) {
+                const int p = e0 >> g.lg_hx, c = 2 * (e0 & (g.hx - 1));
+                const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
+                const auto a0 = fetch(i0);
+                const auto a1 = fetch(i0 + g.nx);
+                const cplx<T>* row = ws + p * g.rowstride;
+                const cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                apply(i0, a0, mk2<T>(z0.re, z1.re));
+                apply(i0 + g.nx, a1, mk2<T>(z0.im, z1.im));
+            }
         }
         ctx.sync();
     }
 }
 
-// Whole convolution; `cluster_sync` separates the phases.  The leading block barrier orders the
-// caller's earlier slab writes (made with a different pixel->thread mapping) before the producer
-// reads them; between two convolutions no cluster barrier is needed because a CTA only rewrites
-// the exchange-buffer rows it alone read in the previous rows_inverse.
-template <class Ctx, typename T, class Prod, class Cons>
-BSGP_DEV void conv_image(Ctx& ctx, const ConvGeom& g, cplx<T>* ws, const cplx<T>* twx, const cplx<T>* twy, cplx<T>* spec,
-                         cplx<T>* tf, int mode, Prod& prod, Cons& cons) {
-    ctx.sync();
-    conv_rows_forward(ctx, g, ws, twx, spec, prod);
-    ctx.cluster_sync();
-    conv_cols(ctx, g, ws, twy, spec, tf, mode);
-    ctx.cluster_sync();
-    if (mode != CONV_MAKE_TF) conv_rows_inverse(ctx, g, ws, twx, spec, cons);
+// elementwise loop over pixel pairs with batched loads: In fetch(i) (loads only), body(i, In), i even
+template <int U, class Ctx, class Fetch, class Body>
+BSGP_DEV void pair_loop(Ctx& ctx, int n, Fetch& fetch, Body& body) {
+    const int np = n >> 1;
+    int q0 = ctx.tid;
+    for (; q0 + (U - 1) * ctx.nt < np; q0 += ctx.nt * U) {          // full batches: no guards, the tile stays in registers
+        decltype(fetch(0)) in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) in[u] = fetch(2 * (q0 + u * ctx.nt));
+#pragma unroll
+        for (int u = 0; u < U; ++u) body(2 * (q0 + u * ctx.nt), in[u]);
+    }
+    for (; q0 < np; q0 += ctx.nt) {
+        const auto in = fetch(2 * q0);
+        body(2 * q0, in);
+    }
 }
 
 }  // namespace bsgp

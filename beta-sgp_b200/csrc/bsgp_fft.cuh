@@ -1,4 +1,4 @@
-// In-place shared-memory FFT building blocks (power-of-two lengths, radix 2/4/8/16 stages).
+// In-place shared-memory FFT building blocks (power-of-two lengths, radix 2/4/8 stages).
 //
 // Replaces the numpy.fft (pocketfft) calls behind the reference's PSF operator,
 // sgp.py:109-117 / 571-579:  real(ifftn(TF * fftn(x))).
@@ -57,7 +57,7 @@ template <bool INV, typename T> BSGP_DEV void dft4(cplx<T>& a0, cplx<T>& a1, cpl
     a3 = csub(t1, t3);
 }
 
-// multiply by exp(-+ 2 pi i m / 16) for the constants needed by the radix-8/16 kernels
+// multiply by exp(-+ 2 pi i m / 16) for the constants needed by the radix-8 kernel
 template <int M16, bool INV, typename T> BSGP_DEV cplx<T> mul_w16(cplx<T> a) {
     const T c1 = (T)0.92387953251128673848, s1 = (T)0.38268343236508978178, c2 = (T)0.70710678118654752440;
     // forward twiddle = (cr, -si); inverse = (cr, +si)
@@ -85,36 +85,10 @@ template <bool INV, typename T> BSGP_DEV void dft8(cplx<T>* v) {
     v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
 
-template <bool INV, typename T> BSGP_DEV void dft16(cplx<T>* v) {
-    // n = 4 n1 + n2, k = k1 + 4 k2
-    dft4<INV>(v[0], v[4], v[8], v[12]);    // n2 = 0 -> Y[0][k1] in v[0], v[4], v[8], v[12]
-    dft4<INV>(v[1], v[5], v[9], v[13]);    // n2 = 1
-    dft4<INV>(v[2], v[6], v[10], v[14]);   // n2 = 2
-    dft4<INV>(v[3], v[7], v[11], v[15]);   // n2 = 3
-    // Y[n2][k1] sits in v[4 k1 + n2]; twiddle by W16^(n2 k1)
-    v[5] = mul_w16<1, INV>(v[5]);   v[6] = mul_w16<2, INV>(v[6]);   v[7] = mul_w16<3, INV>(v[7]);
-    v[9] = mul_w16<2, INV>(v[9]);   v[10] = mul_w16<4, INV>(v[10]); v[11] = mul_w16<6, INV>(v[11]);
-    v[13] = mul_w16<3, INV>(v[13]); v[14] = mul_w16<6, INV>(v[14]); v[15] = mul_w16<9, INV>(v[15]);
-    // outer transforms over n2 for each k1: outputs X[k1 + 4 k2] land in v[4 k1 + k2]
-    dft4<INV>(v[0], v[1], v[2], v[3]);
-    dft4<INV>(v[4], v[5], v[6], v[7]);
-    dft4<INV>(v[8], v[9], v[10], v[11]);
-    dft4<INV>(v[12], v[13], v[14], v[15]);
-    // transpose the 4x4 register tile so that v[q] = X[q]
-    cplx<T> t;
-    t = v[1]; v[1] = v[4]; v[4] = t;
-    t = v[2]; v[2] = v[8]; v[8] = t;
-    t = v[3]; v[3] = v[12]; v[12] = t;
-    t = v[6]; v[6] = v[9]; v[9] = t;
-    t = v[7]; v[7] = v[13]; v[13] = t;
-    t = v[11]; v[11] = v[14]; v[14] = t;
-}
-
 template <int LOG2R, bool INV, typename T> BSGP_DEV void dft_r(cplx<T>* v) {
     if (LOG2R == 1) dft2<INV>(v[0], v[1]);
     else if (LOG2R == 2) dft4<INV>(v[0], v[1], v[2], v[3]);
-    else if (LOG2R == 3) dft8<INV>(v);
-    else dft16<INV>(v);
+    else dft8<INV>(v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -153,10 +127,10 @@ BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftP
     const int lg_per = pl.log2n - LOG2R;          // butterflies per transform
     const int lgS = lgL - LOG2R;
     const int total = nfft << lg_per;
+    const int ps = pl.pad_shift, lg_tw = pl.log2n - lgL;
     for (int t = ctx.tid; t < total; t += ctx.nt) {
         const int f = t >> lg_per, u = t & ((1 << lg_per) - 1);
-        stage_task<LOG2R, INV>(ws + (size_t)f * fstride, pl.pad_shift, lgL, u >> lgS, u & ((1 << lgS) - 1), tw,
-                               pl.log2n - lgL);
+        stage_task<LOG2R, INV>(ws + f * fstride, ps, lgL, u >> lgS, u & ((1 << lgS) - 1), tw, lg_tw);
     }
     ctx.sync();
 }
@@ -167,14 +141,16 @@ BSGP_DEV void dispatch_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const
     switch (lg_r) {
         case 1: run_stage<1, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
         case 2: run_stage<2, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
-        case 3: run_stage<3, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
-        default: run_stage<4, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+        default: run_stage<3, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
     }
 }
 
-// nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout).  Ends with a barrier.
+// nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout), ws = shared memory at byte
+// offset ws_off.  Ends with a barrier.
+// Not inlined: the solver runs five convolutions, all sharing one copy of each direction.
 template <bool INV, class Ctx, typename T>
-BSGP_DEV void fft_batch(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+    cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     if (!INV) {
         int lgL = pl.log2n;
         for (int s = 0; s < pl.nstages; ++s) {

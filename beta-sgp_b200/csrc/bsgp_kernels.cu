@@ -1,20 +1,20 @@
-// libbsgp: persistent thread-block-cluster kernels for the SGP / beta-SGP restoration loop on
-// B200 (sm_100a) and their C ABI (include/bsgp.h).
+// libbsgp: C ABI (include/bsgp.h), plan management and the small stand-alone kernels of the B200
+// (sm_100a) SGP / beta-SGP restoration path.  The persistent cluster solve kernel lives in
+// bsgp_solve_kernel.cuh (instantiated by bsgp_solve_f64.cu / bsgp_solve_f32.cu).
 //
 // Execution model
 //   * One thread-block CLUSTER of G CTAs restores one image from start to finish
 //     (bsgp_solver.cuh); clusters are persistent and pull image indices from a global queue, so
 //     images with very different iteration counts (2..160 observed) never wait for each other and
 //     the host is not involved between "inputs resident" and "outputs written".
-//   * Scalars travel between the CTAs of a cluster through distributed shared memory: every CTA
-//     stores its partial sums into every peer's inbox and one hardware cluster barrier publishes
-//     them; all CTAs then add the G partials in the same order, so all controllers agree bit for bit.
+//   * Scalars travel between the CTAs of a cluster through distributed shared memory
+//     (bsgp_device.cuh).
 //   * Per-image state that does not fit in shared memory lives in a per-CLUSTER scratch area (not
-//     per image): with ~18 clusters in flight the whole working set stays resident in the 126 MB L2,
+//     per image): with ~15 clusters in flight the whole working set stays resident in the 126 MB L2,
 //     HBM only sees each input once and each output once.
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,146 +22,16 @@
 #include <string>
 #include <vector>
 
+#include "bsgp_device.cuh"
+#include "bsgp_launch.h"
 #include "bsgp_plan.h"
 #include "bsgp_solver.cuh"
 
-namespace cg = cooperative_groups;
 using namespace bsgp;
-
-// ------------------------------------------------------------------------------------------------
-// device context
-// ------------------------------------------------------------------------------------------------
-constexpr int kMaxWarps = 32;
-constexpr int kMaxG = 16;
-constexpr int kMaxK = 8;
-
-struct SharedCtl {
-    double warp_part[kMaxWarps][kMaxK];
-    double inbox[2][kMaxG][kMaxK];
-    int next_img;
-    int pad[3];
-};
-
-__device__ __forceinline__ double red_combine(int op, double a, double b) {
-    if (op == 0) return a + b;
-    if (op == 1) return (b < a) ? b : a;
-    return (b > a) ? b : a;
-}
-
-struct DeviceCtx {
-    int tid, nt, rank, G;
-    SharedCtl* sh;
-    int parity;
-
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ void cluster_sync() {
-        if (G > 1) cg::this_cluster().sync();
-        else __syncthreads();
-    }
-    __device__ __forceinline__ double now() {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        return (double)t * 1e-9;
-    }
-    // all-reduce of k <= 8 doubles over the whole cluster; every thread of every CTA receives the
-    // same bits.  One block barrier + one cluster barrier.
-    __device__ __forceinline__ void allreduce(int op, double* v, int k) {
-        const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
-        for (int j = 0; j < k; ++j) {
-            double x = v[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
-            if (lane == 0) sh->warp_part[warp][j] = x;
-        }
-        __syncthreads();
-        if (tid < G * k) {
-            const int dst = tid / k, j = tid - dst * k;
-            double s = sh->warp_part[0][j];
-            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][j]);
-            double* slot = &sh->inbox[parity][rank][j];
-            if (G > 1) slot = cg::this_cluster().map_shared_rank(slot, dst);
-            *slot = s;
-        }
-        cluster_sync();
-        for (int j = 0; j < k; ++j) {
-            double s = sh->inbox[parity][0][j];
-            for (int r = 1; r < G; ++r) s = red_combine(op, s, sh->inbox[parity][r][j]);
-            v[j] = s;
-        }
-        parity ^= 1;
-    }
-    __device__ __forceinline__ void allreduce_sum(double* v, int k) { allreduce(0, v, k); }
-    __device__ __forceinline__ void allreduce_min(double& v) { allreduce(1, &v, 1); }
-    __device__ __forceinline__ void allreduce_max(double& v) { allreduce(2, &v, 1); }
-};
-
-__device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
-    DeviceCtx c;
-    c.tid = threadIdx.x; c.nt = blockDim.x; c.G = G;
-    c.rank = (G > 1) ? (int)cg::this_cluster().block_rank() : 0;
-    c.sh = sh; c.parity = 0;
-    return c;
-}
-
-// next work item for the whole cluster (leader claims it, pushes it into every CTA's shared memory)
-__device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue) {
-    if (ctx.rank == 0 && ctx.tid == 0) {
-        const int v = atomicAdd(queue, 1);
-        if (ctx.G > 1) {
-            cg::cluster_group cl = cg::this_cluster();
-            for (int r = 0; r < ctx.G; ++r) *cl.map_shared_rank(&ctx.sh->next_img, r) = v;
-        } else {
-            ctx.sh->next_img = v;
-        }
-    }
-    ctx.cluster_sync();
-    const int img = ctx.sh->next_img;
-    ctx.cluster_sync();          // nobody may still be reading when the leader claims the next one
-    return img;
-}
-
-template <typename T> struct SmemLayout {
-    SharedCtl* ctl;
-    cplx<T>* ws;
-    unsigned char* bufs;
-};
-template <typename T> __device__ __forceinline__ SmemLayout<T> carve(unsigned char* smem, size_t ws_bytes) {
-    SmemLayout<T> l;
-    l.ctl = reinterpret_cast<SharedCtl*>(smem);
-    size_t off = (sizeof(SharedCtl) + 127) & ~(size_t)127;
-    l.ws = reinterpret_cast<cplx<T>*>(smem + off);
-    off += (ws_bytes + 127) & ~(size_t)127;
-    l.bufs = smem + off;
-    return l;
-}
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const size_t ws_bytes, const size_t tf_stride) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    SmemLayout<T> lay = carve<T>(smem, ws_bytes);
-    DeviceCtx ctx = make_ctx(lay.ctl, a.g.G);
-    const int cluster_id = blockIdx.x / a.g.G;
-    const size_t npix = (size_t)a.g.ny * a.g.nx;
-    const size_t nslab = (size_t)a.g.rows_per_cta * a.g.nx;
-    T* buf[NBUF];
-    size_t soff = 0;
-#pragma unroll
-    for (int b = 0; b < NBUF; ++b) {
-        if (a.resident_mask & (1 << b)) { buf[b] = reinterpret_cast<T*>(lay.bufs + soff); soff += nslab * sizeof(T); }
-        else buf[b] = a.work + (size_t)cluster_id * a.work_stride + (size_t)b * npix + (size_t)ctx.rank * nslab;
-    }
-    cplx<T>* spec = a.spec + (size_t)cluster_id * a.spec_stride;
-    for (;;) {
-        const int img = next_item(ctx, a.queue);
-        if (img >= a.batch) break;
-        cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
-        solve_image<T>(ctx, a, buf, lay.ws, spec, tf, img);
-    }
-}
-
 template <typename T> struct ConvArgs {
     ConvGeom g;
     int count;
@@ -173,32 +43,50 @@ template <typename T> struct ConvArgs {
 };
 
 // mode CONV_MAKE_TF: tf[p] = fftn(fftshift(psf[p])) in workspace order (sgp.py:109); otherwise
-// out[i] = A(in[i]) or A^T(in[i]) (sgp.py:111-120).
+// out[i] = A(in[i]) or A^T(in[i]) (sgp.py:111-120).  Dynamic shared memory: [SharedCtl][ConvGeom][position table][workspace].
 template <typename T>
-__global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, const size_t ws_bytes) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    SmemLayout<T> lay = carve<T>(smem, ws_bytes);
-    DeviceCtx ctx = make_ctx(lay.ctl, a.g.G);
+__global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, const unsigned off_geom, const unsigned off_ppx, const unsigned off_ws) {
+    unsigned char* smem = dyn_smem();
+    DeviceCtx ctx = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
+    ConvGeom* gs = reinterpret_cast<ConvGeom*>(smem + off_geom);
+    unsigned short* ppx = reinterpret_cast<unsigned short*>(smem + off_ppx);
+    if (ctx.tid == 0) *gs = a.g;
+    fill_pos_table(ctx, a.g.px, ppx);
+    __syncthreads();
+    const ConvGeom& g = *gs;
     const int cluster_id = blockIdx.x / a.g.G;
-    const ConvGeom& g = a.g;
-    const size_t npix = (size_t)g.ny * g.nx;
+    const int ny = a.g.ny, nx = a.g.nx;
+    const size_t npix = (size_t)ny * nx;
     cplx<T>* spec = a.spec + (size_t)cluster_id * a.spec_stride;
-    const int r0 = ctx.rank * g.rows_per_cta;
+    const int r0 = ctx.rank * a.g.rows_per_cta;
     for (;;) {
         const int img = next_item(ctx, a.queue);
         if (img >= a.count) break;
         const T* src = a.in + (size_t)img * npix;
         if (a.mode == CONV_MAKE_TF) {
-            auto prod = [&](int row, int c) -> T {
-                return src[(size_t)((r0 + row + (g.ny >> 1)) & (g.ny - 1)) * g.nx + ((c + (g.nx >> 1)) & (g.nx - 1))];
+            const int lg_nx = a.g.lg_nx;
+            auto pf = [&](int i) {
+                const int row = i >> lg_nx, c = i & (nx - 1);
+                In1<T> r; r.a = ld2(src + (size_t)((r0 + row + (ny >> 1)) & (ny - 1)) * nx, (c + (nx >> 1)) & (nx - 1)); return r;
             };
-            auto cons = [&](int, int, T) {};
-            conv_image(ctx, g, lay.ws, a.twx, a.twy, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF, prod, cons);
+            auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+            ctx.sync();
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, off_ppx, spec, pf, pe);
+            ctx.cluster_sync();
+            conv_cols(ctx, gs, off_ws, a.twy, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
-            T* dst = a.out + (size_t)img * npix;
-            auto prod = [&](int row, int c) -> T { return src[(size_t)(r0 + row) * g.nx + c]; };
-            auto cons = [&](int row, int c, T v) { dst[(size_t)(r0 + row) * g.nx + c] = v; };
-            conv_image(ctx, g, lay.ws, a.twx, a.twy, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode, prod, cons);
+            T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
+            const T* s0 = src + (size_t)r0 * nx;
+            auto pf = [&](int i) { In1<T> r; r.a = ld2(s0, i); return r; };
+            auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+            auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
+            auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
+            ctx.sync();
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, off_ppx, spec, pf, pe);
+            ctx.cluster_sync();
+            conv_cols(ctx, gs, off_ws, a.twy, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            ctx.cluster_sync();
+            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, off_ppx, spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -284,12 +172,14 @@ static int fail(int code, const char* fmt, ...) {
 
 struct bsgp_plan {
     int ny = 0, nx = 0, dtype = 0, device = 0;
-    int num_sms = 0, max_smem = 0;
+    int num_sms = 0, max_smem = 0, smem_per_sm = 0;
     int want_G = 0, want_threads = 0;
     bool configured = false;
     ConvGeom g{};
-    size_t ws_bytes = 0, smem_bytes = 0, elem = 8;
-    int threads = 0, minb = 1, num_clusters = 0, resident_mask = 0;
+    size_t ws_bytes = 0, smem_bytes = 0, conv_smem = 0, elem = 8;
+    SmemPlan sp{};
+    unsigned conv_off_geom = 0, conv_off_ppx = 0, conv_off_ws = 0;
+    int threads = 0, minb = 1, num_clusters = 0, conv_clusters = 0, resident_mask = 0;
     void* twx = nullptr; void* twy = nullptr;
     void* tf = nullptr; int n_psf = 0; int tf_capacity = 0; size_t tf_stride = 0;
     void* work = nullptr; size_t work_stride = 0;
@@ -298,49 +188,7 @@ struct bsgp_plan {
     size_t workspace_bytes = 0;
 };
 
-template <typename T> static const void* solve_kernel_ptr(int threads) {
-    if (threads <= 256) return (const void*)bsgp_solve_kernel<T, 256, 2>;
-    return (const void*)bsgp_solve_kernel<T, 512, 1>;
-}
 template <typename T> static const void* conv_kernel_ptr() { return (const void*)bsgp_conv_kernel<T>; }
-
-static int launch_clustered(const void* func, int grid, int block, size_t smem, int G, cudaStream_t st, void** args) {
-    // the attribute is per function, not per plan: plans of different shapes share the kernels, so (re)state
-    // the dynamic shared-memory limit this launch needs
-    CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (G > 8) CU(cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelExC(&cfg, func, args));
-    return BSGP_OK;
-}
-
-static int query_clusters(const void* func, int block, size_t smem, int G, int num_sms, int* out) {
-    CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (G > 8) CU(cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    if (G == 1) {
-        int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, func, block, smem));
-        *out = nb * num_sms;
-        return BSGP_OK;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(G * num_sms); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    CU(cudaOccupancyMaxActiveClusters(&n, func, &cfg));
-    *out = n;
-    return BSGP_OK;
-}
 
 static void plan_free_buffers(bsgp_plan* p) {
     cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue);
@@ -348,9 +196,11 @@ static void plan_free_buffers(bsgp_plan* p) {
     p->tf_capacity = 0; p->n_psf = 0;
 }
 
+static inline size_t up128(size_t v) { return (v + 127) & ~(size_t)127; }
+
 // Residency priority: the two projection buffers (read E times per iteration), then the arrays with
-// the most touches per iteration.
-static const int kResidencyOrder[NBUF] = {B_D, B_T1, B_G, B_XTF, B_DTF, B_GN, B_XA, B_XB, B_BKG};
+// the most touches per iteration; the background image last (unused when the background is a scalar).
+static const int kResidencyOrder[NBUF] = {B_D, B_T1, B_G, B_X, B_XTF, B_DTF, B_GN, B_BKG};
 
 template <typename T> static int plan_setup_t(bsgp_plan* p) {
     const size_t npix = (size_t)p->ny * p->nx;
@@ -365,19 +215,36 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     const size_t nslab = npix / G;
     if (threads <= 0) threads = (nslab <= 2048) ? 256 : 512;
     if (threads != 256 && threads != 512 && threads != 128) return fail(BSGP_E_ARG, "threads must be 128, 256 or 512");
-    const size_t ws_limit = 72 * 1024;
+    const size_t ws_limit = 76 * 1024;
     if (!make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes))
         return fail(BSGP_E_SHAPE, "unsupported shape %dx%d for cluster size %d (power-of-two sides >= 16 required)", p->ny, p->nx, G);
     p->threads = threads;
-    const size_t fixed = ((sizeof(SharedCtl) + 127) & ~(size_t)127) + ((p->ws_bytes + 127) & ~(size_t)127);
-    // shared-memory budget per CTA: whole SM for the big configuration, a third for stamps
-    size_t budget = (size_t)p->max_smem;
-    const size_t slab_bytes = nslab * sizeof(T);
-    if (threads <= 256) {
-        // several CTAs per SM: aim for everything resident, then see how many CTAs fit
-        const size_t all = fixed + NBUF * slab_bytes;
-        budget = all <= (size_t)p->max_smem ? all : (size_t)p->max_smem;
+    p->minb = threads >= 512 ? 1 : (threads >= 256 ? (nslab * sizeof(T) > 16384 ? 1 : 2) : 3);
+    // shared-memory layout: [SharedCtl][ImgState][twiddles][position table][workspace][resident slabs]
+    SmemPlan sp;
+    size_t off = up128(sizeof(SharedCtl));
+    sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
+    const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
+    sp.tw_smem = tw_bytes <= 16384;
+    sp.off_twx = (unsigned)off;
+    sp.off_twy = (unsigned)off;
+    if (sp.tw_smem) {
+        off = up128(off + (size_t)p->nx * sizeof(cplx<T>));
+        if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + (size_t)p->ny * sizeof(cplx<T>)); }
     }
+    sp.off_ppx = (unsigned)off; off = up128(off + (size_t)p->nx * sizeof(unsigned short));
+    sp.off_ws = (unsigned)off; off = up128(off + p->ws_bytes);
+    sp.off_bufs = (unsigned)off;
+    p->sp = sp;
+    const size_t fixed = off;
+    // per-CTA budget: the opt-in maximum, or an equal share of the SM (1 KB per CTA is reserved by the system)
+    size_t budget = (size_t)p->max_smem;
+    if (p->minb > 1) {
+        const size_t share = ((size_t)p->smem_per_sm - (size_t)p->minb * 1024) / p->minb;
+        budget = share < budget ? share : budget;
+        budget &= ~(size_t)127;
+    }
+    const size_t slab_bytes = nslab * sizeof(T);
     size_t used = fixed;
     int mask = 0;
     for (int k = 0; k < NBUF; ++k) {
@@ -385,14 +252,24 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     }
     p->resident_mask = mask;
     p->smem_bytes = used;
-    const void* fn = solve_kernel_ptr<T>(threads);
+    if (p->smem_bytes > (size_t)p->max_smem)
+        return fail(BSGP_E_SHAPE, "shape %dx%d needs %zu B of shared memory per CTA (limit %d)", p->ny, p->nx, p->smem_bytes, p->max_smem);
+    LaunchCfg lc{G * p->num_sms, threads, G, p->smem_bytes, nullptr, p->minb};
     int nc = 0;
-    int rc = query_clusters(fn, threads, p->smem_bytes, G, p->num_sms, &nc);
-    if (rc) return rc;
+    cudaError_t e = query_solve_clusters<T>(lc, p->num_sms, &nc);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     if (nc <= 0) return fail(BSGP_E_CUDA, "kernel does not fit: cluster %d, %d threads, %zu B shared memory", G, threads, p->smem_bytes);
     p->num_clusters = nc;
-    rc = query_clusters(conv_kernel_ptr<T>(), 512, fixed, G, p->num_sms, &nc);
-    if (rc) return rc;
+    // stand-alone convolution kernel: [SharedCtl][ConvGeom][position table][workspace]
+    p->conv_off_geom = (unsigned)up128(sizeof(SharedCtl));
+    p->conv_off_ppx = (unsigned)up128(p->conv_off_geom + sizeof(ConvGeom));
+    p->conv_off_ws = (unsigned)up128(p->conv_off_ppx + (size_t)p->nx * sizeof(unsigned short));
+    p->conv_smem = p->conv_off_ws + up128(p->ws_bytes);
+    LaunchCfg cc{G * p->num_sms, 512, G, p->conv_smem, nullptr};
+    e = query_clusters(conv_kernel_ptr<T>(), cc, p->num_sms, &nc);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    if (nc <= 0) return fail(BSGP_E_CUDA, "convolution kernel does not fit: cluster %d, %zu B shared memory", G, p->conv_smem);
+    p->conv_clusters = nc;
 
     std::vector<cplx<T>> tw;
     make_twiddles<T>(p->nx, tw);
@@ -401,13 +278,14 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     make_twiddles<T>(p->ny, tw);
     CU(cudaMalloc(&p->twy, tw.size() * sizeof(cplx<T>)));
     CU(cudaMemcpy(p->twy, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    const int nscratch = p->num_clusters > p->conv_clusters ? p->num_clusters : p->conv_clusters;
     p->work_stride = NBUF * npix;
     p->spec_stride = (size_t)p->ny * p->g.hx;
     p->tf_stride = (size_t)(p->g.hx + 1) * p->ny;
     CU(cudaMalloc(&p->work, (size_t)p->num_clusters * p->work_stride * sizeof(T)));
-    CU(cudaMalloc(&p->spec, (size_t)p->num_clusters * p->spec_stride * sizeof(cplx<T>)));
+    CU(cudaMalloc(&p->spec, (size_t)nscratch * p->spec_stride * sizeof(cplx<T>)));
     CU(cudaMalloc((void**)&p->queue, sizeof(int)));
-    p->workspace_bytes = (size_t)p->num_clusters * (p->work_stride * sizeof(T) + p->spec_stride * sizeof(cplx<T>));
+    p->workspace_bytes = (size_t)p->num_clusters * p->work_stride * sizeof(T) + (size_t)nscratch * p->spec_stride * sizeof(cplx<T>);
     p->configured = true;
     return BSGP_OK;
 }
@@ -416,6 +294,17 @@ static int plan_setup(bsgp_plan* p) {
     if (p->configured) return BSGP_OK;
     CU(cudaSetDevice(p->device));
     return p->dtype == BSGP_F64 ? plan_setup_t<double>(p) : plan_setup_t<float>(p);
+}
+
+template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int count, cudaStream_t st) {
+    CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
+    const int nclu = count < p->conv_clusters ? count : p->conv_clusters;
+    LaunchCfg lc{nclu * p->g.G, 512, p->g.G, p->conv_smem, st};
+    unsigned og = p->conv_off_geom, op = p->conv_off_ppx, ow = p->conv_off_ws;
+    void* args[] = {&a, &og, &op, &ow};
+    cudaError_t e = launch_clustered(conv_kernel_ptr<T>(), lc, args);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "convolution kernel launch failed: %s", cudaGetErrorString(e));
+    return BSGP_OK;
 }
 
 template <typename T> static int set_psf_t(bsgp_plan* p, const void* psf_dev, int n_psf, cudaStream_t st) {
@@ -430,12 +319,7 @@ template <typename T> static int set_psf_t(bsgp_plan* p, const void* psf_dev, in
     a.g = p->g; a.count = n_psf; a.in = (const T*)psf_dev; a.out = nullptr;
     a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = n_psf; a.tf_stride = p->tf_stride;
     a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride; a.mode = CONV_MAKE_TF; a.queue = p->queue;
-    CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
-    const size_t smem = ((sizeof(SharedCtl) + 127) & ~(size_t)127) + ((p->ws_bytes + 127) & ~(size_t)127);
-    size_t wsb = p->ws_bytes;
-    void* args[] = {&a, &wsb};
-    const int nclu = n_psf < p->num_clusters ? n_psf : p->num_clusters;
-    return launch_clustered(conv_kernel_ptr<T>(), nclu * p->g.G, 512, smem, p->g.G, st, args);
+    return launch_conv<T>(p, a, n_psf, st);
 }
 
 template <typename T> static int apply_psf_t(bsgp_plan* p, const void* x, void* y, int batch, int adjoint, cudaStream_t st) {
@@ -444,12 +328,7 @@ template <typename T> static int apply_psf_t(bsgp_plan* p, const void* x, void* 
     a.g = p->g; a.count = batch; a.in = (const T*)x; a.out = (T*)y;
     a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = p->n_psf; a.tf_stride = p->tf_stride;
     a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride; a.mode = adjoint ? CONV_CTF : CONV_TF; a.queue = p->queue;
-    CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
-    const size_t smem = ((sizeof(SharedCtl) + 127) & ~(size_t)127) + ((p->ws_bytes + 127) & ~(size_t)127);
-    size_t wsb = p->ws_bytes;
-    void* args[] = {&a, &wsb};
-    const int nclu = batch < p->num_clusters ? batch : p->num_clusters;
-    return launch_clustered(conv_kernel_ptr<T>(), nclu * p->g.G, 512, smem, p->g.G, st, args);
+    return launch_conv<T>(p, a, batch, st);
 }
 
 template <typename T>
@@ -468,11 +347,14 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     a.tr_beta = out->trace_beta; a.tr_trials = out->trace_trials; a.tr_evals = out->trace_evals;
     a.queue = p->queue;
     CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
-    size_t wsb = p->ws_bytes, tfs = p->tf_stride;
-    void* args[] = {&a, &wsb, &tfs};
     const int nclu = batch < p->num_clusters ? batch : p->num_clusters;
-    return launch_clustered(solve_kernel_ptr<T>(p->threads), nclu * p->g.G, p->threads, p->smem_bytes, p->g.G, st, args);
+    LaunchCfg lc{nclu * p->g.G, p->threads, p->g.G, p->smem_bytes, st, p->minb};
+    cudaError_t e = launch_solve<T>(lc, a, p->sp, p->tf_stride);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "solve kernel launch failed: %s", cudaGetErrorString(e));
+    return BSGP_OK;
 }
+
+static inline bool misaligned(const void* p) { return ((uintptr_t)p & 15) != 0; }
 
 static int check_params(const bsgp_params* q) {
     if (q->divergence != BSGP_DIV_KL && q->divergence != BSGP_DIV_BETA) return fail(BSGP_E_ARG, "bad divergence");
@@ -511,6 +393,7 @@ int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan) {
     p->ny = ny; p->nx = nx; p->dtype = dtype; p->device = device;
     p->num_sms = prop.multiProcessorCount;
     p->max_smem = (int)prop.sharedMemPerBlockOptin;
+    p->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     int rc = plan_setup(p);
     if (rc) { plan_free_buffers(p); delete p; return rc; }
     *plan = p;
@@ -547,6 +430,7 @@ int bsgp_plan_get_info(const bsgp_plan* p, bsgp_plan_info* info) {
 
 int bsgp_set_psf(bsgp_plan* p, const void* psf_dev, int n_psf, void* stream) {
     if (!p || !psf_dev || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (misaligned(psf_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
     return p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, (cudaStream_t)stream)
                                 : set_psf_t<float>(p, psf_dev, n_psf, (cudaStream_t)stream);
@@ -576,6 +460,8 @@ int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp
     if (prm->divergence == BSGP_DIV_BETA && !in->beta0) return fail(BSGP_E_ARG, "beta-divergence needs inputs.beta0");
     if (prm->init_recon == 1 && !in->x0) return fail(BSGP_E_ARG, "init_recon = 1 needs inputs.x0");
     if (prm->errflag && (!in->obj || !out->err)) return fail(BSGP_E_ARG, "errflag needs inputs.obj and outputs.err");
+    if (misaligned(in->gn) || misaligned(out->x) || misaligned(in->x0) || misaligned(in->obj) || (in->bkg_is_image && misaligned(in->bkg)))
+        return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
     return p->dtype == BSGP_F64 ? solve_t<double>(p, prm, batch, in, out, (cudaStream_t)stream)
                                 : solve_t<float>(p, prm, batch, in, out, (cudaStream_t)stream);
@@ -640,6 +526,7 @@ int bsgp_apply_psf(bsgp_plan* p, const void* x_dev, void* y_dev, int batch, int 
     if (!p || !x_dev || !y_dev || batch < 1) return fail(BSGP_E_ARG, "bad argument");
     if (p->n_psf < 1) return fail(BSGP_E_STATE, "bsgp_set_psf has not been called");
     if (p->n_psf != 1 && p->n_psf != batch) return fail(BSGP_E_STATE, "%d PSFs set; need 1 or batch (%d)", p->n_psf, batch);
+    if (misaligned(x_dev) || misaligned(y_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
     return p->dtype == BSGP_F64 ? apply_psf_t<double>(p, x_dev, y_dev, batch, adjoint, (cudaStream_t)stream)
                                 : apply_psf_t<float>(p, x_dev, y_dev, batch, adjoint, (cudaStream_t)stream);

@@ -12,24 +12,25 @@ namespace bsgp {
 inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// Stage radices: every stage has an in-block stride >= 8 (conflict-free 16-byte quarter-warp
-// access) except the last, whose radix (8 or 16) sets the padding period.
+// Stage radices (2, 4 or 8: a radix-8 butterfly of complex doubles fits a 128-register thread): every
+// stage has an in-block stride >= 8 (conflict-free 16-byte quarter-warp access) except the last,
+// whose radix (8) sets the padding period.
 inline bool make_fft_plan(int n, FftPlan* pl) {
-    static const int table[16][5] = {
+    static const int table[16][6] = {
         {0}, {0}, {0},
-        {3, 0},            // 8
-        {4, 0},            // 16
-        {2, 3, 0},         // 32   = 4 x 8
-        {3, 3, 0},         // 64   = 8 x 8
-        {3, 4, 0},         // 128  = 8 x 16
-        {4, 4, 0},         // 256  = 16 x 16
-        {3, 3, 3, 0},      // 512
-        {3, 3, 4, 0},      // 1024
-        {3, 4, 4, 0},      // 2048
-        {4, 4, 4, 0},      // 4096
-        {3, 3, 3, 4, 0},   // 8192
-        {3, 3, 4, 4, 0},   // 16384
-        {3, 4, 4, 4, 0}};  // 32768
+        {3, 0},              // 8
+        {1, 3, 0},           // 16   = 2 x 8
+        {2, 3, 0},           // 32   = 4 x 8
+        {3, 3, 0},           // 64   = 8 x 8
+        {2, 2, 3, 0},        // 128  = 4 x 4 x 8
+        {2, 3, 3, 0},        // 256  = 4 x 8 x 8
+        {3, 3, 3, 0},        // 512
+        {2, 2, 3, 3, 0},     // 1024
+        {2, 3, 3, 3, 0},     // 2048
+        {3, 3, 3, 3, 0},     // 4096
+        {2, 2, 3, 3, 3, 0},  // 8192
+        {2, 3, 3, 3, 3, 0},  // 16384
+        {3, 3, 3, 3, 3, 0}}; // 32768
     if (!is_pow2(n) || n < 8 || n > 32768) return false;
     pl->n = n;
     pl->log2n = ilog2(n);

@@ -1,0 +1,7 @@
+// fp32 instantiation of the persistent solve kernel (optional reduced-precision mode).
+#include "bsgp_solve_kernel.cuh"
+
+namespace bsgp {
+template cudaError_t launch_solve<float>(const LaunchCfg&, const SolveArgs<float>&, const SmemPlan&, size_t);
+template cudaError_t query_solve_clusters<float>(const LaunchCfg&, int, int*);
+}  // namespace bsgp

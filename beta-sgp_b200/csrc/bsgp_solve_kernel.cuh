@@ -1,0 +1,72 @@
+// The persistent solve kernel and its launchers.  Included by one translation unit per data type
+// (bsgp_solve_f64.cu, bsgp_solve_f32.cu) so the two compile in parallel.
+#pragma once
+#include <string.h>
+
+#include "bsgp_device.cuh"
+#include "bsgp_launch.h"
+#include "bsgp_solver.cuh"
+
+namespace bsgp {
+
+template <typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
+    unsigned char* smem = dyn_smem();
+    DeviceCtx ctx = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
+    ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);
+    const int cluster_id = blockIdx.x / a.g.G;
+    const size_t npix = (size_t)a.g.ny * a.g.nx;
+    const size_t nslab = (size_t)a.g.rows_per_cta * a.g.nx;
+    T* buf[NBUF];
+    size_t soff = sp.off_bufs;
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) {
+        if (a.resident_mask & (1 << b)) { buf[b] = reinterpret_cast<T*>(smem + soff); soff += nslab * sizeof(T); }
+        else buf[b] = a.work + (size_t)cluster_id * a.work_stride + (size_t)b * npix + (size_t)ctx.rank * nslab;
+    }
+    cplx<T>* twx_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twx);
+    cplx<T>* twy_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twy);
+    if (sp.tw_smem) {
+        for (int k = ctx.tid; k < a.g.nx; k += ctx.nt) twx_s[k] = a.twx[k];
+        if (sp.off_twy != sp.off_twx) for (int k = ctx.tid; k < a.g.ny; k += ctx.nt) twy_s[k] = a.twy[k];
+    }
+    unsigned short* ppx = reinterpret_cast<unsigned short*>(smem + sp.off_ppx);
+    fill_pos_table(ctx, a.g.px, ppx);
+    if (ctx.tid == 0) {
+        S->geom = a.g;
+        S->ppx_off = sp.off_ppx;
+        S->ws_off = sp.off_ws;
+        S->spec = a.spec + (size_t)cluster_id * a.spec_stride;
+        S->twx = sp.tw_smem ? twx_s : a.twx;
+        S->twy = sp.tw_smem ? twy_s : a.twy;
+    }
+    __syncthreads();
+    for (;;) {
+        const int img = next_item(ctx, a.queue);
+        if (img >= a.batch) break;
+        cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
+        solve_image<T>(ctx, a, S, buf, tf, img);
+    }
+}
+
+// register budgets: 512 x 128, 256 x 255 (one CTA per SM: big slabs), 256 x 128 (two CTAs per SM), 128 x 168 (three)
+template <typename T> static const void* solve_kernel_ptr(int threads, int minb) {
+    if (threads <= 128) return (const void*)bsgp_solve_kernel<T, 128, 3>;
+    if (threads <= 256) return minb >= 2 ? (const void*)bsgp_solve_kernel<T, 256, 2> : (const void*)bsgp_solve_kernel<T, 256, 1>;
+    return (const void*)bsgp_solve_kernel<T, 512, 1>;
+}
+
+template <typename T>
+cudaError_t launch_solve(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride) {
+    SolveArgs<T> args = a;
+    SmemPlan plan = sp;
+    size_t tfs = tf_stride;
+    void* params[] = {&args, &plan, &tfs};
+    return launch_clustered(solve_kernel_ptr<T>(lc.threads, lc.minb), lc, params);
+}
+
+template <typename T> cudaError_t query_solve_clusters(const LaunchCfg& lc, int num_sms, int* out) {
+    return query_clusters(solve_kernel_ptr<T>(lc.threads, lc.minb), lc, num_sms, out);
+}
+
+}  // namespace bsgp

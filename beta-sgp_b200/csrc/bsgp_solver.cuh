@@ -3,11 +3,20 @@
 // This is the body of the persistent solve kernel: every loop of the reference (outer iteration
 // sgp.py:302-425 / 748-882, line search :328-349 / :776-800, projection root-find
 // flux_conserve_proj.py:38-142) runs here with ordinary control flow.  All threads of all CTAs of
-// the cluster execute the scalar controller redundantly on bit-identical all-reduced sums, so the
-// control flow is uniform across the cluster and no scalar is ever broadcast or sent to the host.
+// the cluster execute the scalar controller (`solve_image`) redundantly on bit-identical
+// all-reduced sums, so the control flow is uniform across the cluster and no scalar is ever
+// broadcast or sent to the host.
+//
+// Structure.  The controller is inlined into the kernel; every pass over the pixels is a separate
+// NON-inlined "phase" function (ph_*), so each pass gets its own register allocation (no spills
+// from the controller's long-lived state) and the kernel stays small enough for the instruction
+// cache.  Phases read the per-image constants (`ImgState`, one copy per CTA in shared memory), take
+// the few changing scalars by value and return their partial sums by value; the controller does the
+// cluster all-reduce.  Each phase starts with a block barrier because consecutive phases map
+// pixels to threads differently.
 //
 // `Ctx` supplies: tid, nt, rank, G, sync(), cluster_sync(), allreduce_sum(double*, k),
-// allreduce_min(double&), allreduce_max(double&), now().  DeviceCtx (bsgp_kernels.cu) is the
+// allreduce_min(double&), allreduce_max(double&), now().  DeviceCtx (bsgp_device.cuh) is the
 // product; tests/host_emul provides a one-thread emulation of the same code.
 //
 // Numerics follow the reference's operand order with non-contracted arithmetic (bsgp_math.cuh);
@@ -22,7 +31,7 @@
 
 namespace bsgp {
 
-enum Buf { B_GN = 0, B_BKG, B_XA, B_XB, B_G, B_XTF, B_D, B_DTF, B_T1, NBUF };
+enum Buf { B_GN = 0, B_BKG, B_X, B_G, B_XTF, B_D, B_DTF, B_T1, NBUF };
 constexpr int kMaxMem = 16;
 
 template <typename T> struct SolveArgs {
@@ -42,6 +51,23 @@ template <typename T> struct SolveArgs {
     double* tr_alpha; double* tr_lambda; double* tr_beta; int* tr_trials; int* tr_evals;
     int* queue;
 };
+
+// Per-image constants of one CTA (shared memory).  Pointers address this CTA's slab of each array.
+template <typename T> struct ImgState {
+    T* gn; T* bkg; T* x; T* g; T* xtf; T* d; T* dtf; T* t1;
+    const T* gn_raw; const T* bkg_raw; const T* x0_raw; const T* truth; T* x_out;
+    const cplx<T>* twx; const cplx<T>* twy; cplx<T>* spec; cplx<T>* tf;
+    unsigned ws_off, ppx_off;        // FFT workspace and position table: byte offsets into dynamic shared memory
+    ConvGeom geom;
+    int nslab, bkg_img, init_recon, has_cap, pflag, want_err, stop2;
+    T bkg_raw_s, scaling, bkg_s, null_fill, x_const, cap, xlo, xhi;
+};
+
+struct R2 { double a, b; };
+struct R3 { double a, b, c; };
+struct R7 { double v[7]; };
+
+enum { F_PENDING = 1, F_XONES = 2, F_FIRST = 4 };
 
 // divergence constants for the current beta (sgp.py:452-458)
 template <typename T> struct DivK {
@@ -120,127 +146,493 @@ template <typename T> BSGP_DEV T clip_bounds(T v, T lo, T hi) {   // sgp.py:355-
     return v;
 }
 
+// x(lambda) of the projection: min(cap, max(0, (c + lambda) * X))      flux_conserve_proj.py:22-24
+template <typename T> BSGP_DEV T proj_point(T c, T X, T lam, bool has_cap, T cap) {
+    T v = nmul(nadd(c, lam), X);
+    v = (v <= (T)0) ? (T)0 : v;
+    if (has_cap) v = (v >= cap) ? cap : v;
+    return v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// setup phases (sgp.py:166-217, 248-257)
+// -------------------------------------------------------------------------------------------------
+// sum(gn), sum(gn - bkg), max(gn) over the raw slab
+template <typename T, class Ctx> BSGP_NOINLINE R3 ph_stats(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    const T* gr = S->gn_raw; const T* br = S->bkg_raw; const bool bimg = S->bkg_img != 0; const T bs = S->bkg_raw_s;
+    double mx = -INFINITY, s0 = 0.0, s1 = 0.0;
+    auto fetch = [&](int i) { In2<T> r; r.a = ld2(gr, i); r.b = bimg ? ld2(br, i) : mk2(bs, bs); return r; };
+    auto body = [&](int, const In2<T>& in) {
+        mx = ((double)in.a.x > mx) ? (double)in.a.x : mx;
+        s0 += (double)in.a.x;
+        s1 += (double)nsub(in.a.x, in.b.x);
+        mx = ((double)in.a.y > mx) ? (double)in.a.y : mx;
+        s0 += (double)in.a.y;
+        s1 += (double)nsub(in.a.y, in.b.y);
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+    R3 r; r.a = s0; r.b = s1; r.c = mx;
+    return r;
+}
+
+// gn = gn_raw / scaling; returns the smallest positive scaled value
+template <typename T, class Ctx> BSGP_NOINLINE double ph_scale_gn(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    const T* gr = S->gn_raw; T* gn = S->gn; const T scaling = S->scaling;
+    double vmin = INFINITY;
+    auto fetch = [&](int i) { In1<T> r; r.a = ld2(gr, i); return r; };
+    auto body = [&](int i, const In1<T>& in) {
+        const V2<T> v = mk2(ndiv(in.a.x, scaling), ndiv(in.a.y, scaling));
+        st2(gn, i, v);
+        if (v.x > (T)0 && (double)v.x < vmin) vmin = (double)v.x;
+        if (v.y > (T)0 && (double)v.y < vmin) vmin = (double)v.y;
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+    return vmin;
+}
+
+// null-pixel fix, scaled background, start image; returns sum(gn - bkg)
+template <typename T, class Ctx> BSGP_NOINLINE double ph_init(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    T* gn = S->gn; T* bkgb = S->bkg; T* x = S->x; const T* br = S->bkg_raw; const T* x0 = S->x0_raw;
+    const bool bimg = S->bkg_img != 0; const int init = S->init_recon;
+    const T scaling = S->scaling, null_fill = S->null_fill, bkg_s = S->bkg_s, x_const = S->x_const;
+    double sum = 0.0;
+    auto fetch = [&](int i) {
+        In3<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(br, i) : mk2(bkg_s, bkg_s); r.c = (init == 1) ? ld2(x0, i) : mk2((T)0, (T)0);
+        return r;
+    };
+    auto one = [&](T v0, T braw, T x0v, T& gfix, T& bk, T& xv) {
+        gfix = (v0 <= (T)0) ? null_fill : v0;
+        bk = bimg ? ndiv(braw, scaling) : bkg_s;
+        sum += (double)nsub(gfix, bk);
+        if (init == 0) xv = (T)0;
+        else if (init == 1) xv = ndiv(x0v, scaling);
+        else if (init == 2) xv = v0;                      // gn.copy() before the null-pixel fix (sgp.py:171)
+        else xv = x_const;
+    };
+    auto body = [&](int i, const In3<T>& in) {
+        V2<T> gf, bk, xv;
+        one(in.a.x, in.b.x, in.c.x, gf.x, bk.x, xv.x);
+        one(in.a.y, in.b.y, in.c.y, gf.y, bk.y, xv.y);
+        if (in.a.x <= (T)0 || in.a.y <= (T)0) st2(gn, i, gf);
+        if (bimg) st2(bkgb, i, bk);
+        st2(x, i, xv);
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+    return sum;
+}
+
+// initial projection, step 1: pflag 0 -> x = max(x, 0); pflag 1 -> c = x, X = 1
+template <typename T, class Ctx> BSGP_NOINLINE void ph_proj_init_load(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    T* x = S->x; T* cbuf = S->d; T* Xbuf = S->t1; const bool pflag = S->pflag != 0;
+    auto fetch = [&](int i) { In1<T> r; r.a = ld2(x, i); return r; };
+    auto body = [&](int i, const In1<T>& in) {
+        if (pflag) { st2(cbuf, i, in.a); st2(Xbuf, i, mk2((T)1, (T)1)); }
+        else st2(x, i, mk2((in.a.x < (T)0) ? (T)0 : in.a.x, (in.a.y < (T)0) ? (T)0 : in.a.y));
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+}
+
+// r(lambda) + b = sum_i x_i(lambda) over the slab                       flux_conserve_proj.py:22-25
+template <typename T, class Ctx> BSGP_NOINLINE double ph_proj_eval(Ctx ctx, const ImgState<T>* S, T lam) {
+    ctx.sync();
+    const T* cbuf = S->d; const T* Xbuf = S->t1; const bool has_cap = S->has_cap != 0; const T cap = S->cap;
+    double s = 0.0;
+    auto fetch = [&](int i) { In2<T> r; r.a = ld2(cbuf, i); r.b = ld2(Xbuf, i); return r; };
+    auto body = [&](int, const In2<T>& in) {
+        s += (double)proj_point(in.a.x, in.b.x, lam, has_cap, cap);
+        s += (double)proj_point(in.a.y, in.b.y, lam, has_cap, cap);
+    };
+    pair_loop<8>(ctx, S->nslab, fetch, body);
+    return s;
+}
+
+template <typename T, class Ctx> BSGP_NOINLINE void ph_proj_init_store(Ctx ctx, const ImgState<T>* S, T lam) {
+    ctx.sync();
+    const T* cbuf = S->d; T* x = S->x; const bool has_cap = S->has_cap != 0; const T cap = S->cap;
+    auto fetch = [&](int i) { In1<T> r; r.a = ld2(cbuf, i); return r; };
+    auto body = [&](int i, const In1<T>& in) {
+        st2(x, i, mk2(proj_point(in.a.x, (T)1, lam, has_cap, cap), proj_point(in.a.y, (T)1, lam, has_cap, cap)));
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+}
+
+// errflag, iteration 0: |x - obj|^2, |obj|^2                            sgp.py:240-244, 255-257
+template <typename T, class Ctx> BSGP_NOINLINE R2 ph_err0(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    const T* truth = S->truth; const T* x = S->x; const T scaling = S->scaling;
+    double e0 = 0.0, e1 = 0.0;
+    auto fetch = [&](int i) { In2<T> r; r.a = ld2(truth, i); r.b = ld2(x, i); return r; };
+    auto one = [&](T tr, T xv) {
+        const T t = ndiv(tr, scaling);
+        const T e = nsub(xv, t);
+        e0 += (double)nmul(e, e);
+        e1 += (double)nmul(t, t);
+    };
+    auto body = [&](int, const In2<T>& in) { one(in.a.x, in.b.x); one(in.a.y, in.b.y); };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+    R2 r; r.a = e0; r.b = e1;
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// row passes of the PSF operator with the neighbouring elementwise work fused in
+// -------------------------------------------------------------------------------------------------
+// producer: plain copy of x (which = 0) or gn (which = 1)
+template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const ImgState<T>* S, int which) {
+    ctx.sync();
+    const T* src = which ? S->gn : S->x;
+    auto pf = [&](int i) { In1<T> r; r.a = ld2(src, i); return r; };
+    auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+}
+
+// consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
+template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+    const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    auto cf = [&](int i) { In2<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
+    auto ca = [&](int i, const In2<T>& in, V2<T> v) {
+        st2(xtf, i, v);
+        V2<T> p;
+        p.x = objective_pixel(dk, in.a.x, nadd(v.x, in.b.x), v.x, want_s1 != 0, acc);
+        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, acc);
+        st2(t1, i, p);
+    };
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    return r;
+}
+
+// producer of the gradient's A^T argument: gn/den (KL, cached) or gn*den^(beta-2) = gn*(den^(beta-1)/den).
+// Unless F_FIRST, the accepted step is applied to x_tf on the way (x_tf += lam*d_tf, sgp.py:340).
+template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx, const ImgState<T>* S, int kind, T lam, int flags) {
+    ctx.sync();
+    const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; const T* dtf = S->dtf; const T* t1 = S->t1;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const bool first = (flags & F_FIRST) != 0;
+    auto pf = [&](int i) {
+        In5<T> r; r.a = ld2(xtf, i); r.b = first ? mk2((T)0, (T)0) : ld2(dtf, i); r.c = ld2(t1, i);
+        r.d = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.e = ld2(gn, i); return r;
+    };
+    auto pe = [&](int i, const In5<T>& in) -> V2<T> {
+        V2<T> xt = in.a;
+        if (!first) { xt = mk2(nadd(in.a.x, nmul(lam, in.b.x)), nadd(in.a.y, nmul(lam, in.b.y))); st2(xtf, i, xt); }
+        if (kind == 0) return in.c;
+        return mk2(nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))), nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))));
+    };
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+}
+
+// consumer: g = 1 - w (KL) or den^(beta-1) - w                            sgp.py:262 / 705
+template <typename T, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx, const ImgState<T>* S, int kind) {
+    const T* t1 = S->t1; T* gr = S->g;
+    auto cf = [&](int i) { In1<T> r; r.a = ld2(t1, i); return r; };
+    auto ca = [&](int i, const In1<T>& in, V2<T> w) {
+        st2(gr, i, (kind == 0) ? mk2(nsub((T)1, w.x), nsub((T)1, w.y)) : mk2(nsub(in.a.x, w.x), nsub(in.a.y, w.y)));
+    };
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+}
+
+// consumer: bounds of the scaling matrix from y = flux/(flux+bkg) * A^T(gn)     sgp.py:268-270 / 712-714
+template <typename T, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const ImgState<T>* S, double flux) {
+    const T* bkgb = S->bkg; const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    double lo = INFINITY, hi = -INFINITY;
+    auto cf = [&](int i) { In1<T> r; r.a = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
+    auto one = [&](T b, T w) {
+        const T ratio = (T)ndiv(flux, nadd(flux, (double)b));
+        const double yv = (double)nmul(ratio, w);
+        if (yv > 0.0 && yv < lo) lo = yv;
+        if (yv > hi) hi = yv;
+    };
+    auto ca = [&](int, const In1<T>& in, V2<T> w) { one(in.a.x, w.x); one(in.a.y, w.y); };
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    R2 r; r.a = lo; r.b = hi;
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// iteration phases (sgp.py:302-425 / 748-882)
+// -------------------------------------------------------------------------------------------------
+// proj_type 1: (pending x update,) X = clip(x), c = (x - alpha X g) / X           sgp.py:311-316
+template <typename T, class Ctx> BSGP_NOINLINE void ph_trial_point(Ctx ctx, const ImgState<T>* S, T al, T lam_pending, int flags) {
+    ctx.sync();
+    T* x = S->x; const T* gr = S->g; T* cbuf = S->d; T* Xbuf = S->t1;
+    const T xlo = S->xlo, xhi = S->xhi;
+    const bool pending = (flags & F_PENDING) != 0, ones = (flags & F_XONES) != 0;
+    auto fetch = [&](int i) { In3<T> r; r.a = ld2(x, i); r.b = ld2(gr, i); r.c = pending ? ld2(cbuf, i) : mk2((T)0, (T)0); return r; };
+    auto one = [&](T xv, T gv, T dv, T& xo, T& co, T& Xo) {
+        if (pending) xv = nadd(xv, nmul(lam_pending, dv));
+        const T X = ones ? (T)1 : clip_bounds(xv, xlo, xhi);
+        const T y = nsub(xv, nmul(al, nmul(X, gv)));
+        xo = xv; co = nmul(y, ndiv((T)1, X)); Xo = X;
+    };
+    auto body = [&](int i, const In3<T>& in) {
+        V2<T> xo, co, Xo;
+        one(in.a.x, in.b.x, in.c.x, xo.x, co.x, Xo.x);
+        one(in.a.y, in.b.y, in.c.y, xo.y, co.y, Xo.y);
+        if (pending) st2(x, i, xo);
+        st2(cbuf, i, co);
+        st2(Xbuf, i, Xo);
+    };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+}
+
+// producer of A(d): d = y - x with y the projected trial point; returns the slab part of gd = d.g   sgp.py:311-321
+template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const ImgState<T>* S, T al, T lam_proj, T lam_pending, int flags) {
+    ctx.sync();
+    T* x = S->x; const T* gr = S->g; T* dbuf = S->d; const T* Xbuf = S->t1;
+    const T xlo = S->xlo, xhi = S->xhi, cap = S->cap;
+    const bool has_cap = S->has_cap != 0, pflag = S->pflag != 0;
+    const bool pending = (flags & F_PENDING) != 0, ones = (flags & F_XONES) != 0;
+    double gd = 0.0;
+    auto pf = [&](int i) {
+        In4<T> r; r.a = ld2(x, i); r.b = ld2(gr, i);
+        r.c = (pflag || pending) ? ld2(dbuf, i) : mk2((T)0, (T)0);
+        r.d = pflag ? ld2(Xbuf, i) : mk2((T)0, (T)0);
+        return r;
+    };
+    auto one = [&](T xv, T gv, T cv, T Xv, T& xo) -> T {
+        T y;
+        if (pflag) {
+            y = proj_point(cv, Xv, lam_proj, has_cap, cap);
+        } else {
+            if (pending) xv = nadd(xv, nmul(lam_pending, cv));
+            const T X = ones ? (T)1 : clip_bounds(xv, xlo, xhi);
+            y = nsub(xv, nmul(al, nmul(X, gv)));
+            y = (y < (T)0) ? (T)0 : y;
+        }
+        xo = xv;
+        const T d = nsub(y, xv);
+        gd += (double)nmul(d, gv);
+        return d;
+    };
+    auto pe = [&](int i, const In4<T>& in) -> V2<T> {
+        V2<T> xo, d;
+        d.x = one(in.a.x, in.b.x, in.c.x, in.d.x, xo.x);
+        d.y = one(in.a.y, in.b.y, in.c.y, in.d.y, xo.y);
+        if (!pflag && pending) st2(x, i, xo);
+        st2(dbuf, i, d);
+        return d;
+    };
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+    return gd;
+}
+
+// consumer of A(d): d_tf, first line-search trial (lam = 1) fused            sgp.py:326-334
+template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+    const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    auto cf = [&](int i) { In3<T> r; r.a = ld2(xtf, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.c = ld2(gn, i); return r; };
+    auto ca = [&](int i, const In3<T>& in, V2<T> v) {
+        st2(dtf, i, v);
+        V2<T> p;
+        const T xt0 = nadd(in.a.x, v.x);                   // lam = 1
+        p.x = objective_pixel(dk, in.c.x, nadd(xt0, in.b.x), xt0, want_s1 != 0, acc);
+        const T xt1 = nadd(in.a.y, v.y);
+        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, acc);
+        st2(t1, i, p);
+    };
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    return r;
+}
+
+// slab part of sum dD_beta/dbeta at the rejected trial point               sgp.py:798-800
+template <typename T, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx, const ImgState<T>* S, T lam, T b) {
+    ctx.sync();
+    const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    double db = 0.0;
+    auto fetch = [&](int i) {
+        In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
+    };
+    auto body = [&](int, const In4<T>& in) {
+        db += (double)dbeta_pixel(in.d.x, nadd(nadd(in.a.x, nmul(lam, in.b.x)), in.c.x), b);
+        db += (double)dbeta_pixel(in.d.y, nadd(nadd(in.a.y, nmul(lam, in.b.y)), in.c.y), b);
+    };
+    pair_loop<1>(ctx, S->nslab, fetch, body);
+    return db;
+}
+
+// one more line-search trial: objective at x_tf + lam d_tf                  sgp.py:329-334
+template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk, int want_s1) {
+    ctx.sync();
+    const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    auto fetch = [&](int i) {
+        In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
+    };
+    auto body = [&](int i, const In4<T>& in) {
+        V2<T> p;
+        const T xt0 = nadd(in.a.x, nmul(lam, in.b.x));
+        p.x = objective_pixel(dk, in.d.x, nadd(xt0, in.c.x), xt0, want_s1 != 0, acc);
+        const T xt1 = nadd(in.a.y, nmul(lam, in.b.y));
+        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, acc);
+        st2(t1, i, p);
+    };
+    pair_loop<2>(ctx, S->nslab, fetch, body);
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    return r;
+}
+
+// consumer of A^T(.): new gradient, y_k, Barzilai-Borwein sums, stop-rule / error sums   sgp.py:343-365, 394-402
+template <typename T, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgState<T>* S, T lam, int kind) {
+    const T* t1 = S->t1; T* gr = S->g; const T* dbuf = S->d; const T* x = S->x; const T* truth = S->truth;
+    const T xlo = S->xlo, xhi = S->xhi, scaling = S->scaling;
+    const bool want_err = S->want_err != 0, stop2 = S->stop2 != 0;
+    double bb[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) bb[k] = 0.0;
+    auto cf = [&](int i) {
+        In5<T> r; r.a = ld2(t1, i); r.b = ld2(gr, i); r.c = ld2(dbuf, i); r.d = ld2(x, i);
+        r.e = want_err ? ld2(truth, i) : mk2((T)0, (T)0); return r;
+    };
+    auto one = [&](T p1, T gold, T dv, T xv, T tr, T w) -> T {
+        const T gnew = (kind == 0) ? nsub((T)1, w) : nsub(p1, w);
+        const T yk = nsub(gnew, gold);
+        const T sk = nmul(lam, dv);
+        const T xn = nadd(xv, sk);                                // x + lam*d (:329,337)
+        const T X = clip_bounds(xn, xlo, xhi);
+        const T sk2 = nmul(sk, ndiv((T)1, X));
+        const T yk2 = nmul(yk, X);
+        bb[0] += (double)sk2 * (double)yk;
+        bb[1] += (double)yk2 * (double)sk;
+        bb[2] += (double)sk2 * (double)sk2;
+        bb[3] += (double)yk2 * (double)yk2;
+        if (stop2) { bb[4] += (double)sk * (double)sk; bb[5] += (double)xn * (double)xn; }
+        if (want_err) { const T e = nsub(xn, ndiv(tr, scaling)); bb[6] += (double)nmul(e, e); }
+        return gnew;
+    };
+    auto ca = [&](int i, const In5<T>& in, V2<T> w) {
+        V2<T> gnew;
+        gnew.x = one(in.a.x, in.b.x, in.c.x, in.d.x, in.e.x, w.x);
+        gnew.y = one(in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
+        st2(gr, i, gnew);
+    };
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    R7 r;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r.v[k] = bb[k];
+    return r;
+}
+
+// x_out = x * scaling                                                        sgp.py:428
+template <typename T, class Ctx> BSGP_NOINLINE void ph_store_out(Ctx ctx, const ImgState<T>* S) {
+    ctx.sync();
+    const T* x = S->x; T* out = S->x_out; const T scaling = S->scaling;
+    auto fetch = [&](int i) { In1<T> r; r.a = ld2(x, i); return r; };
+    auto body = [&](int i, const In1<T>& in) { st2(out, i, mk2(nmul(in.a.x, scaling), nmul(in.a.y, scaling))); };
+    pair_loop<4>(ctx, S->nslab, fetch, body);
+}
+
+// the two column passes between a producer and a consumer
+template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgState<T>* S, cplx<T>* tf, int mode) {
+    ctx.cluster_sync();
+    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->spec, tf, mode);
+    ctx.cluster_sync();
+}
+
+// -------------------------------------------------------------------------------------------------
+// the controller
+// -------------------------------------------------------------------------------------------------
 template <typename T, class Ctx>
-BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T>* ws, cplx<T>* spec, cplx<T>* tf, int img) {
+BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* const* buf, cplx<T>* tf, int img) {
     const bsgp_params& P = a.p;
-    const ConvGeom& g = a.g;
-    const int nx = g.nx, lg_nx = g.lg_nx;
-    const int nslab = g.rows_per_cta * nx;
-    const size_t npix = (size_t)g.ny * nx;
+    const int nslab = a.g.rows_per_cta * a.g.nx;
+    const size_t npix = (size_t)a.g.ny * a.g.nx;
     const double npix_d = (double)npix;
     const size_t goff = (size_t)img * npix + (size_t)ctx.rank * nslab;
     const size_t toff = (size_t)img * (P.maxit + 1);
     const bool leader = (ctx.rank == 0 && ctx.tid == 0);
     const bool pflag = P.proj_type == 1;
     const bool is_beta = P.divergence == BSGP_DIV_BETA;
-
-    T* gn = buf[B_GN]; T* bkgb = buf[B_BKG]; T* xcur = buf[B_XA]; T* xnext = buf[B_XB]; T* gr = buf[B_G];
-    T* xtf = buf[B_XTF]; T* dbuf = buf[B_D]; T* dtf = buf[B_DTF]; T* t1 = buf[B_T1];
-    const T* gn_raw = a.gn + goff;
     const bool bkg_img = a.bkg_is_image != 0;
-    const T* bkg_raw_img = bkg_img ? a.bkg + goff : nullptr;
+    const bool want_err = P.errflag && a.obj != nullptr && a.err != nullptr;
     const T bkg_raw_s = bkg_img ? (T)0 : a.bkg[img];
     const double t_start = ctx.now();
 
+    ctx.sync();                      // the previous image's last phase may still be reading S
+    if (ctx.tid == 0) {
+        S->gn = buf[B_GN]; S->bkg = buf[B_BKG]; S->x = buf[B_X]; S->g = buf[B_G];
+        S->xtf = buf[B_XTF]; S->d = buf[B_D]; S->dtf = buf[B_DTF]; S->t1 = buf[B_T1];
+        S->gn_raw = a.gn + goff;
+        S->bkg_raw = bkg_img ? a.bkg + goff : a.gn + goff;             // never dereferenced when !bkg_img
+        S->x0_raw = (P.init_recon == 1) ? a.x0 + goff : a.gn + goff;
+        S->truth = want_err ? a.obj + goff : a.gn + goff;
+        S->x_out = a.x_out + goff;
+        S->tf = tf;
+        S->nslab = nslab; S->bkg_img = bkg_img; S->init_recon = P.init_recon; S->has_cap = P.has_sat != 0;
+        S->pflag = pflag; S->want_err = want_err; S->stop2 = (P.stop_criterion == 2);
+        S->bkg_raw_s = bkg_raw_s;
+    }
+
     // ------------------------------------------------------------------ setup (sgp.py:166-217)
     double v3[3];
-    double mx = -INFINITY;
-    v3[0] = v3[1] = 0.0;
-    for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-        const T v = gn_raw[i];
-        mx = ((double)v > mx) ? (double)v : mx;
-        v3[0] += (double)v;
-        v3[1] += (double)nsub(v, bkg_img ? bkg_raw_img[i] : bkg_raw_s);
-    }
+    const R3 st = ph_stats<T>(ctx, S);
+    v3[0] = st.a; v3[1] = st.b;
+    double mx = st.c;
     ctx.allreduce_sum(v3, 2);
     ctx.allreduce_max(mx);
     const double sum_raw = v3[0], sum_gb_raw = v3[1];
     const T scaling = P.scale_data ? (T)mx : (T)1;
     const T bkg_s = ndiv(bkg_raw_s, scaling);
+    if (ctx.tid == 0) { S->scaling = scaling; S->bkg_s = bkg_s; }
 
-    double vmin = INFINITY;
-    for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-        const T v = ndiv(gn_raw[i], scaling);
-        gn[i] = v;
-        if (v > (T)0 && (double)v < vmin) vmin = (double)v;
-    }
+    double vmin = ph_scale_gn<T>(ctx, S);
     ctx.allreduce_min(vmin);
     const T eps = Eps<T>::v();
-    const T null_fill = nmul(nmul((T)vmin, eps), eps);
     const double flux_in = P.has_flux ? a.flux[img] : 0.0;
-    const T x_const = ndiv(nmul((T)ndiv(P.has_flux ? flux_in : sum_gb_raw, npix_d), (T)1), scaling);
-    v3[0] = 0.0;
-    for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-        T v = gn[i];
-        if (v <= (T)0) { v = null_fill; gn[i] = v; }
-        T bk = bkg_s;
-        if (bkg_img) { bk = ndiv(bkg_raw_img[i], scaling); bkgb[i] = bk; }
-        v3[0] += (double)nsub(v, bk);
-        T xv;
-        if (P.init_recon == 0) xv = (T)0;
-        else if (P.init_recon == 1) xv = ndiv(a.x0[goff + i], scaling);
-        else if (P.init_recon == 2) xv = ndiv(gn_raw[i], scaling);
-        else xv = x_const;
-        xcur[i] = xv;
+    const bool has_cap = P.has_sat != 0;
+    if (ctx.tid == 0) {
+        S->null_fill = nmul(nmul((T)vmin, eps), eps);
+        S->x_const = ndiv(nmul((T)ndiv(P.has_flux ? flux_in : sum_gb_raw, npix_d), (T)1), scaling);
+        S->cap = has_cap ? nsub(ndiv((T)P.ccd_sat_level, scaling), eps) : (T)0;
+        S->xlo = (T)0; S->xhi = (T)0;
     }
+    v3[0] = ph_init<T>(ctx, S);
     ctx.allreduce_sum(v3, 1);
     const double flux = P.has_flux ? ndiv(flux_in, (double)scaling) : v3[0];
-    auto bkgv = [&](int i) -> T { return bkg_img ? bkgb[i] : bkg_s; };
 
     double tol = 0.0;                                                   // sgp.py:185-190, 291-294
     if (P.stop_criterion == 2 || P.stop_criterion == 3) tol = P.tol_convergence;
     else if (P.stop_criterion == 4) tol = 1.0 + 1.0 / (sum_raw / npix_d);
     if (P.verbose && P.stop_criterion == 2) tol = nmul(tol, tol);
     const double discr_coeff = nmul(2.0 / npix_d, (double)scaling);
-    const bool has_cap = P.has_sat != 0;
-    const T cap = has_cap ? nsub(ndiv((T)P.ccd_sat_level, scaling), eps) : (T)0;
 
     int status = BSGP_ST_OK;
     int total_evals = 0, total_trials = 0;
     if (pflag && !(flux > 0.0 && is_finite(flux))) status = BSGP_ST_BAD_FLUX;
 
-    // x(lambda) of the projection for slab pixel i: min(cap, max(0, (c + lambda) * X))
-    auto proj_point = [&](T c, T X, T lam) -> T {
-        T v = nmul(nadd(c, lam), X);
-        v = (v <= (T)0) ? (T)0 : v;
-        if (has_cap) v = (v >= cap) ? cap : v;
-        return v;
-    };
-    T* cbuf = dbuf;   // c = y * D during the root-find, then d in place
-    T* Xbuf = t1;     // scaling-matrix diagonal during the root-find, objective cache afterwards
     auto proj_eval = [&](double lam) -> double {
-        double s = 0.0;
-        const T l = (T)lam;
-        for (int i = ctx.tid; i < nslab; i += ctx.nt) s += (double)proj_point(cbuf[i], Xbuf[i], l);
+        double s = ph_proj_eval<T>(ctx, S, (T)lam);
         ctx.allreduce_sum(&s, 1);
         return s - flux;
     };
 
     // ------------------------------------------------------------------ initial projection (:248-253)
     if (status == BSGP_ST_OK) {
-        if (!pflag) {
-            for (int i = ctx.tid; i < nslab; i += ctx.nt) { const T v = xcur[i]; xcur[i] = (v < (T)0) ? (T)0 : v; }
-        } else {
-            for (int i = ctx.tid; i < nslab; i += ctx.nt) { cbuf[i] = xcur[i]; Xbuf[i] = (T)1; }
+        ph_proj_init_load<T>(ctx, S);
+        if (pflag) {
             const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
             total_evals += pr.evals;
             if (pr.status != PROJ_OK) status = BSGP_ST_PROJ_NO_BRACKET;
-            const T l = (T)pr.lambda;
-            for (int i = ctx.tid; i < nslab; i += ctx.nt) xcur[i] = proj_point(cbuf[i], (T)1, l);
+            ph_proj_init_store<T>(ctx, S, (T)pr.lambda);
         }
     }
 
     double truth_sq = 1.0;
-    const bool want_err = P.errflag && a.obj != nullptr && a.err != nullptr;
-    const T* truth = want_err ? a.obj + goff : nullptr;
     if (want_err && status == BSGP_ST_OK) {                             // :240-244, 255-257
-        double e2[2] = {0.0, 0.0};
-        for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-            const T t = ndiv(truth[i], scaling);
-            const T e = nsub(xcur[i], t);
-            e2[0] += (double)nmul(e, e);
-            e2[1] += (double)nmul(t, t);
-        }
+        const R2 e = ph_err0<T>(ctx, S);
+        double e2[2] = {e.a, e.b};
         ctx.allreduce_sum(e2, 2);
         truth_sq = e2[1];
         if (leader) a.err[(size_t)img * (P.maxit + 2)] = sqrt(e2[0] / truth_sq);
@@ -251,58 +643,34 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
     double s1 = 0.0;          // sum k*gn^beta for the current beta
     bool s1_valid = false;
     double fv = 0.0, x_low = 0.0, x_upp = 0.0;
-    KSum osum[3];
     double acc[4];
 
     if (status == BSGP_ST_OK) {
         // ---------------------------------------------------------------- x_tf = A(x), objective (:260-265)
-        osum[0].clear(); osum[1].clear(); osum[2].clear();
+        ph_rf_copy<T>(ctx, S, 0);
+        conv_middle<T>(ctx, S, tf, CONV_TF);
         {
-            auto prod = [&](int row, int c) -> T { return xcur[(row << lg_nx) + c]; };
-            auto cons = [&](int row, int c, T v) {
-                const int i = (row << lg_nx) + c;
-                xtf[i] = v;
-                const T den = nadd(v, bkgv(i));
-                t1[i] = objective_pixel(dk, gn[i], den, v, !s1_valid, osum);
-            };
-            conv_image(ctx, g, ws, a.twx, a.twy, spec, tf, CONV_TF, prod, cons);
+            const R3 o = ph_ri_obj0<T>(ctx, S, dk, !s1_valid);
+            acc[0] = o.a; acc[1] = o.b; acc[2] = o.c;
         }
-        acc[0] = osum[0].value(); acc[1] = osum[1].value(); acc[2] = osum[2].value();
         ctx.allreduce_sum(acc, 3);
         if (dk.kind == 1) { s1 = acc[0]; s1_valid = true; }
         fv = objective_value(dk, acc, s1, flux, npix_d);
         // ---------------------------------------------------------------- gradient
-        {
-            auto prod = [&](int row, int c) -> T {
-                const int i = (row << lg_nx) + c;
-                if (dk.kind == 0) return t1[i];
-                const T den = nadd(xtf[i], bkgv(i));
-                return nmul(gn[i], ndiv(t1[i], den));
-            };
-            auto cons = [&](int row, int c, T w) {
-                const int i = (row << lg_nx) + c;
-                gr[i] = (dk.kind == 0) ? nsub((T)1, w) : nsub(t1[i], w);
-            };
-            conv_image(ctx, g, ws, a.twx, a.twy, spec, tf, CONV_CTF, prod, cons);
-        }
+        ph_rf_grad<T>(ctx, S, dk.kind, (T)0, F_FIRST);
+        conv_middle<T>(ctx, S, tf, CONV_CTF);
+        ph_ri_grad0<T>(ctx, S, dk.kind);
         // ---------------------------------------------------------------- scaling-matrix bounds (:268-273)
-        double lo = INFINITY, hi = -INFINITY;
-        {
-            auto prod = [&](int row, int c) -> T { return gn[(row << lg_nx) + c]; };
-            auto cons = [&](int row, int c, T w) {
-                const int i = (row << lg_nx) + c;
-                const T ratio = (T)ndiv(flux, nadd(flux, (double)bkgv(i)));
-                const double yv = (double)nmul(ratio, w);
-                if (yv > 0.0 && yv < lo) lo = yv;
-                if (yv > hi) hi = yv;
-            };
-            conv_image(ctx, g, ws, a.twx, a.twy, spec, tf, CONV_CTF, prod, cons);
-        }
+        ph_rf_copy<T>(ctx, S, 1);
+        conv_middle<T>(ctx, S, tf, CONV_CTF);
+        const R2 lh = ph_ri_bounds<T>(ctx, S, flux);
+        double lo = lh.a, hi = lh.b;
         ctx.allreduce_min(lo);
         ctx.allreduce_max(hi);
         if (!(lo < INFINITY)) status = BSGP_ST_EMPTY_BOUNDS;
         x_low = lo; x_upp = hi;
         if (x_upp / x_low < 50.0) { x_low = x_low / 10.0; x_upp = x_upp * 10.0; }
+        if (ctx.tid == 0) { S->xlo = (T)x_low; S->xhi = (T)x_upp; }
     }
 
     if (leader) {
@@ -317,11 +685,13 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
     double alpha_hist[kMaxMem], f_hist[kMaxMem];      // Valpha / Fold (sgp.py:214-215); dynamically indexed -> local memory
     for (int k = 0; k < MA; ++k) alpha_hist[k] = P.alpha_max;
     for (int k = 0; k < M; ++k) f_hist[k] = -1e30;
-    const T xlo = (T)x_low, xhi = (T)x_upp;
     bool X_is_ones = (P.init_recon == 0);
     int iter = 1;
     bool keep_going = (status == BSGP_ST_OK);
-    T* x_final = xcur;
+    // The accepted step x <- x + lam*d is applied lazily at the start of the NEXT iteration, so when
+    // the loop stops x still holds the previous iterate, which is what the reference returns (:424-425).
+    bool pending = false;
+    T lam_pending = (T)0;
 
     while (keep_going) {
         // history shift (:306-308)
@@ -332,16 +702,13 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
 
         // ---- trial point y = x - alpha X g, projection (:311-318)
         const T al = (T)alpha;
+        int flags = (pending ? F_PENDING : 0) | (X_is_ones ? F_XONES : 0);
         int evals = 0;
         T lam_proj = (T)0;
         if (pflag) {
-            for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-                const T xv = xcur[i];
-                const T X = X_is_ones ? (T)1 : clip_bounds(xv, xlo, xhi);
-                const T y = nsub(xv, nmul(al, nmul(X, gr[i])));
-                cbuf[i] = nmul(y, ndiv((T)1, X));
-                Xbuf[i] = X;
-            }
+            ph_trial_point<T>(ctx, S, al, lam_pending, flags);
+            pending = false;
+            flags &= ~F_PENDING;
             const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
             evals = pr.evals;
             total_evals += evals;
@@ -351,36 +718,14 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
 
         // ---- d = y - x, gd = d.g, d_tf = A(d) with the first line-search trial fused (:318-334)
         double sums[4];   // [0..2] objective terms, [3] gd
-        osum[0].clear(); osum[1].clear(); osum[2].clear();
-        double gd_part = 0.0;
         double lam = 1.0;
+        sums[3] = ph_rf_dir<T>(ctx, S, al, lam_proj, lam_pending, flags);
+        pending = false;
+        conv_middle<T>(ctx, S, tf, CONV_TF);
         {
-            auto prod = [&](int row, int c) -> T {
-                const int i = (row << lg_nx) + c;
-                const T xv = xcur[i], gv = gr[i];
-                T y;
-                if (pflag) {
-                    y = proj_point(cbuf[i], Xbuf[i], lam_proj);
-                } else {
-                    const T X = X_is_ones ? (T)1 : clip_bounds(xv, xlo, xhi);
-                    y = nsub(xv, nmul(al, nmul(X, gv)));
-                    y = (y < (T)0) ? (T)0 : y;
-                }
-                const T d = nsub(y, xv);
-                dbuf[i] = d;
-                gd_part += (double)nmul(d, gv);
-                return d;
-            };
-            auto cons = [&](int row, int c, T v) {
-                const int i = (row << lg_nx) + c;
-                dtf[i] = v;
-                const T xt = nadd(xtf[i], v);                 // lam = 1
-                const T den = nadd(xt, bkgv(i));
-                t1[i] = objective_pixel(dk, gn[i], den, xt, !s1_valid, osum);
-            };
-            conv_image(ctx, g, ws, a.twx, a.twy, spec, tf, CONV_TF, prod, cons);
+            const R3 o = ph_ri_trial<T>(ctx, S, dk, !s1_valid);
+            sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
         }
-        sums[0] = osum[0].value(); sums[1] = osum[1].value(); sums[2] = osum[2].value(); sums[3] = gd_part;
         ctx.allreduce_sum(sums, 4);
         const double gd = sums[3];
         if (dk.kind == 1 && !s1_valid) { s1 = sums[0]; s1_valid = true; }
@@ -391,12 +736,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
         // ---- backtracking (:328-349 / :776-800): accept iff fv <= fr + gamma*lam*gd or lam < 1e-12
         while (!(fv <= nadd(f_ref, nmul(nmul(P.gamma, lam), gd)) || lam < 1e-12)) {
             if (is_beta && P.adapt_beta && dk.kind == 1) {               // :798-800, den of the rejected trial
-                double db = 0.0;
-                const T l = (T)lam;
-                for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-                    const T den = nadd(nadd(xtf[i], nmul(l, dtf[i])), bkgv(i));
-                    db += (double)dbeta_pixel(gn[i], den, dk.b);
-                }
+                double db = ph_dbeta<T>(ctx, S, (T)lam, dk.b);
                 ctx.allreduce_sum(&db, 1);
                 beta_p = nsub(beta_p, nmul(lr, db / npix_d));
                 dk = make_divk<T>(P.divergence, beta_p);
@@ -404,54 +744,19 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
             }
             lam = nmul(lam, P.ls_beta);
             ++trials;
-            osum[0].clear(); osum[1].clear(); osum[2].clear();
-            const T l = (T)lam;
-            for (int i = ctx.tid; i < nslab; i += ctx.nt) {
-                const T xt = nadd(xtf[i], nmul(l, dtf[i]));
-                const T den = nadd(xt, bkgv(i));
-                t1[i] = objective_pixel(dk, gn[i], den, xt, !s1_valid, osum);
-            }
-            sums[0] = osum[0].value(); sums[1] = osum[1].value(); sums[2] = osum[2].value();
+            const R3 o = ph_trial<T>(ctx, S, (T)lam, dk, !s1_valid);
+            sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             ctx.allreduce_sum(sums, 3);
             if (dk.kind == 1 && !s1_valid) { s1 = sums[0]; s1_valid = true; }
             fv = objective_value(dk, sums, s1, flux, npix_d);
         }
         total_trials += trials;
 
-        // ---- accept: x, x_tf, new gradient through A^T, BB sums (:337-347, 355-365, 402)
-        double bb[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) bb[k] = 0.0;
-        {
-            const T l = (T)lam;
-            auto prod = [&](int row, int c) -> T {
-                const int i = (row << lg_nx) + c;
-                xnext[i] = nadd(xcur[i], nmul(l, dbuf[i]));
-                const T xt = nadd(xtf[i], nmul(l, dtf[i]));
-                xtf[i] = xt;
-                if (dk.kind == 0) return t1[i];
-                const T den = nadd(xt, bkgv(i));
-                return nmul(gn[i], ndiv(t1[i], den));
-            };
-            auto cons = [&](int row, int c, T w) {
-                const int i = (row << lg_nx) + c;
-                const T gnew = (dk.kind == 0) ? nsub((T)1, w) : nsub(t1[i], w);
-                const T yk = nsub(gnew, gr[i]);
-                gr[i] = gnew;
-                const T sk = nmul(l, dbuf[i]);
-                const T xn = xnext[i];
-                const T X = clip_bounds(xn, xlo, xhi);
-                const T sk2 = nmul(sk, ndiv((T)1, X));
-                const T yk2 = nmul(yk, X);
-                bb[0] += (double)sk2 * (double)yk;
-                bb[1] += (double)yk2 * (double)sk;
-                bb[2] += (double)sk2 * (double)sk2;
-                bb[3] += (double)yk2 * (double)yk2;
-                if (P.stop_criterion == 2) { bb[4] += (double)sk * (double)sk; bb[5] += (double)xn * (double)xn; }
-                if (want_err) { const T e = nsub(xn, ndiv(truth[i], scaling)); bb[6] += (double)nmul(e, e); }
-            };
-            conv_image(ctx, g, ws, a.twx, a.twy, spec, tf, CONV_CTF, prod, cons);
-        }
+        // ---- accept: x_tf, new gradient through A^T, BB sums (:337-347, 355-365, 402); x itself is updated lazily
+        ph_rf_grad<T>(ctx, S, dk.kind, (T)lam, 0);
+        conv_middle<T>(ctx, S, tf, CONV_CTF);
+        R7 bbr = ph_ri_bb<T>(ctx, S, (T)lam, dk.kind);
+        double* bb = bbr.v;
         ctx.allreduce_sum(bb, 7);
         X_is_ones = false;
 
@@ -497,12 +802,11 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, T* const* buf, cplx<T
             if (a.tr_evals) a.tr_evals[o] = evals;
             if (want_err && iter <= P.maxit + 1) a.err[(size_t)img * (P.maxit + 2) + iter] = sqrt(bb[6] / truth_sq);   // :394-396
         }
-        if (keep_going) { T* t = xcur; xcur = xnext; xnext = t; }       // else: the previous iterate is returned (:424-425)
+        if (keep_going) { pending = true; lam_pending = (T)lam; }       // else: the previous iterate is returned (:424-425)
     }
-    x_final = xcur;
 
     // ------------------------------------------------------------------ epilogue (:427-438)
-    for (int i = ctx.tid; i < nslab; i += ctx.nt) a.x_out[goff + i] = nmul(x_final[i], scaling);
+    ph_store_out<T>(ctx, S);
     if (leader) {
         a.iters[img] = iter - 1;
         a.status[img] = status;

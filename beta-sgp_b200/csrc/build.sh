@@ -1,7 +1,18 @@
 #!/bin/bash
 # Build libbsgp.so in-tree for B200 (sm_100a).  Used by __graft_entry__.build().
+# Three translation units (C ABI + small kernels, fp64 solver, fp32 solver) compile in parallel.
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-$NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-      -Xcompiler -fPIC -shared -o libbsgp.so bsgp_kernels.cu "$@"
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $BSGP_NVCC_FLAGS"
+mkdir -p build
+pids=()
+for tu in bsgp_kernels bsgp_solve_f64 bsgp_solve_f32; do
+    $NVCC $FLAGS -c -o build/$tu.o $tu.cu > build/$tu.log 2>&1 &
+    pids+=($!)
+done
+rc=0
+for pid in "${pids[@]}"; do wait $pid || rc=1; done
+cat build/*.log
+[ $rc -eq 0 ] || exit 1
+$NVCC -shared -o libbsgp.so build/bsgp_kernels.o build/bsgp_solve_f64.o build/bsgp_solve_f32.o

@@ -28,14 +28,21 @@ struct HostCtx {
 template <typename T> struct HostPlan {
     ConvGeom g;
     size_t ws_bytes;
-    std::vector<cplx<T>> twx, twy, ws, spec, tf;
+    std::vector<cplx<T>> twx, twy, spec, tf;
+    std::vector<unsigned char> arena;      // emulated dynamic shared memory: [position table][workspace]
+    unsigned ws_off = 0, ppx_off = 0;
+    void bind() { g_emul_smem = arena.data(); }
     bool init(int ny, int nx, int G, size_t ws_limit) {
         if (!make_geom(ny, nx, G, sizeof(cplx<T>), ws_limit, &g, &ws_bytes)) return false;
         make_twiddles<T>(nx, twx);
         make_twiddles<T>(ny, twy);
-        ws.assign(ws_bytes / sizeof(cplx<T>) + 16, cmake<T>(0, 0));
         spec.assign((size_t)ny * g.hx, cmake<T>(0, 0));
         tf.assign((size_t)(g.hx + 1) * ny, cmake<T>(0, 0));
+        ws_off = (unsigned)(((size_t)nx * sizeof(unsigned short) + 127) & ~(size_t)127);
+        arena.assign(ws_off + ws_bytes + 256, 0);
+        bind();
+        HostCtx ctx;
+        fill_pos_table(ctx, g.px, smem_at<unsigned short>(ppx_off));
         return true;
     }
     void make_tf(const T* psf) {
@@ -44,11 +51,13 @@ template <typename T> struct HostPlan {
             for (int r = 0; r < g.G; ++r) {
                 HostCtx ctx; ctx.rank = r; ctx.G = g.G;
                 const int r0 = r * g.rows_per_cta;
-                auto prod = [&](int row, int c) -> T {
-                    return psf[(size_t)((r0 + row + ny / 2) & (ny - 1)) * nx + ((c + nx / 2) & (nx - 1))];
+                auto pf = [&](int i) {
+                    const int row = i / nx, c = i % nx;
+                    In1<T> q; q.a = ld2(psf + (size_t)((r0 + row + ny / 2) & (ny - 1)) * nx, (c + nx / 2) & (nx - 1)); return q;
                 };
-                if (phase == 0) conv_rows_forward(ctx, g, ws.data(), twx.data(), spec.data(), prod);
-                else conv_cols(ctx, g, ws.data(), twy.data(), spec.data(), tf.data(), CONV_MAKE_TF);
+                auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), pf, pe);
+                else conv_cols(ctx, &g, ws_off, twy.data(), spec.data(), tf.data(), CONV_MAKE_TF);
             }
     }
     void apply(const T* x, T* y, int adjoint) {
@@ -57,11 +66,14 @@ template <typename T> struct HostPlan {
             for (int r = 0; r < g.G; ++r) {
                 HostCtx ctx; ctx.rank = r; ctx.G = g.G;
                 const int r0 = r * g.rows_per_cta;
-                auto prod = [&](int row, int c) -> T { return x[(size_t)(r0 + row) * nx + c]; };
-                auto cons = [&](int row, int c, T v) { y[(size_t)(r0 + row) * nx + c] = v; };
-                if (phase == 0) conv_rows_forward(ctx, g, ws.data(), twx.data(), spec.data(), prod);
-                else if (phase == 1) conv_cols(ctx, g, ws.data(), twy.data(), spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
-                else conv_rows_inverse(ctx, g, ws.data(), twx.data(), spec.data(), cons);
+                const size_t off = (size_t)r0 * nx;
+                auto pf = [&](int i) { In1<T> q; q.a = ld2(x + off, i); return q; };
+                auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+                auto cf = [&](int) { In1<T> q; q.a = mk2((T)0, (T)0); return q; };
+                auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(y + off, i, v); };
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), pf, pe);
+                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
+                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), cf, ca);
             }
     }
 };
@@ -79,8 +91,9 @@ int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after
     for (int f = 0; f < nfft; ++f)
         for (int i = 0; i < n; ++i) ws[(size_t)f * stride + fpad(i, pl.pad_shift)] = cmake<double>(in[2 * ((size_t)f * n + i)], in[2 * ((size_t)f * n + i) + 1]);
     HostCtx ctx;
-    fft_batch<false>(ctx, ws.data(), nfft, stride, pl, tw.data());
-    if (inverse_after) fft_batch<true>(ctx, ws.data(), nfft, stride, pl, tw.data());
+    g_emul_smem = reinterpret_cast<unsigned char*>(ws.data());
+    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data());
+    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data());
     for (int f = 0; f < nfft; ++f)
         for (int k = 0; k < n; ++k) {
             const int p = inverse_after ? k : pos_of_freq(pl, k);
@@ -131,7 +144,11 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
     a.tr_evals = tr_evals;
     HostCtx ctx;
-    solve_image<double>(ctx, a, buf, pl.ws.data(), pl.spec.data(), pl.tf.data(), 0);
+    ImgState<double> S;
+    memset(&S, 0, sizeof(S));
+    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data();
+    pl.bind();
+    solve_image<double>(ctx, a, &S, buf, pl.tf.data(), 0);
     return 0;
 }
 
