@@ -239,6 +239,9 @@ def main():
     trials = res.ls_trials.cpu().numpy().astype(np.float64)
     status = res.status.cpu().numpy()
     assert (status == 0).all(), "solver reported a failure status"
+    # share of (clusters in flight x kernel time) spent inside solves: 1 - this is queue tail + launch overhead
+    t_img = res.times.cpu().numpy()[np.arange(B), res.iters.cpu().numpy().astype(int)]
+    slot_util = float(t_img.sum() / (min(info["num_clusters"], B) * kernel_ms * 1e-3))
     x_sum = res.x.sum(dim=(1, 2)).cpu().numpy()
     assert np.abs(x_sum - w["flux"]).max() <= 1e-8 * np.abs(w["flux"]).max() or args.dtype == "float32", "flux not conserved"
 
@@ -299,7 +302,8 @@ def main():
                        "l2": f"inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed); per-cluster scratch "
                              f"{info['workspace_bytes'] / 1e6:.0f} MB is L2-resident by design",
                        "mean_iterations": float(iters.mean()), "mean_proj_evals_per_iter": float(evals.sum() / iters.sum()),
-                       "mean_trials_per_iter": float(trials.sum() / iters.sum())},
+                       "mean_trials_per_iter": float(trials.sum() / iters.sum()), "max_iterations": int(iters.max()),
+                       "cluster_slot_utilisation": slot_util},
             "ms_per_image_iteration": ms * 1e-3 * 1e3 / (total_iters * args.steps) if total_iters else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "bsgp_solve_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbsgp.so")
+LIB_PATH = os.environ.get("BSGP_LIB") or os.path.join(_HERE, "csrc", "libbsgp.so")   # BSGP_LIB: kernel experiments only
 
 BSGP_F64, BSGP_F32 = 0, 1
 DIV_KL, DIV_BETA = 0, 1
@@ -38,7 +38,7 @@ class Params(C.Structure):
 
 class Inputs(C.Structure):
     _fields_ = [("gn", C.c_void_p), ("bkg", C.c_void_p), ("bkg_is_image", C.c_int), ("flux", C.c_void_p),
-                ("beta0", C.c_void_p), ("x0", C.c_void_p), ("obj", C.c_void_p)]
+                ("beta0", C.c_void_p), ("x0", C.c_void_p), ("obj", C.c_void_p), ("order", C.c_void_p)]
 
 
 class Outputs(C.Structure):

@@ -23,6 +23,7 @@ constexpr int kMaxK = 8;
 struct SharedCtl {
     double warp_part[kMaxWarps][kMaxK];
     double inbox[2][kMaxG][kMaxK];
+    unsigned long long mbar[2];     // transaction barriers of the two inbox halves (cluster all-reduce)
     int next_img;
     int pad[3];
 };
@@ -33,10 +34,17 @@ __device__ __forceinline__ double red_combine(int op, double a, double b) {
     return (b > a) ? b : a;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_to_rank(unsigned addr, int rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
 struct DeviceCtx {
     int tid, nt, rank, G;
     SharedCtl* sh;
-    int parity;
+    int parity;        // bit 0: inbox half in use; bits 1, 2: phase of mbar[0], mbar[1]
 
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void cluster_sync() {
@@ -48,10 +56,15 @@ struct DeviceCtx {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         return (double)t * 1e-9;
     }
-    // all-reduce of k <= 8 doubles over the whole cluster; every thread of every CTA receives the
-    // same bits.  One block barrier + one cluster barrier.
+    // All-reduce of k <= 8 doubles over the whole cluster; every thread of every CTA receives the same
+    // bits (the G partials are combined in rank order everywhere).  One block barrier, then the
+    // partials travel as asynchronous distributed-shared-memory stores that complete a transaction
+    // barrier in the destination CTA (st.async ... mbarrier::complete_tx): no cluster-wide hardware
+    // barrier, no GPU-scope fence, no L1 invalidation.  Safe reuse of the two inbox halves: a CTA can
+    // be at most one reduction ahead of a peer, because it needs that peer's partials to finish one.
     __device__ __forceinline__ void allreduce(int op, double* v, int k) {
         const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+        const int half = parity & 1;
         for (int j = 0; j < k; ++j) {
             double x = v[j];
 #pragma unroll
@@ -59,18 +72,61 @@ struct DeviceCtx {
             if (lane == 0) sh->warp_part[warp][j] = x;
         }
         __syncthreads();
+#ifdef BSGP_OPT_TREE
+        // warp 0 combines the per-warp partials with a fixed shuffle tree (same order in every CTA) and sends them
+        const unsigned bar = smem_u32(&sh->mbar[half]);
+        if (warp == 0) {
+            const double ident = (op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+            const unsigned slot0 = (G > 1 && lane < G) ? map_to_rank(smem_u32(&sh->inbox[half][rank][0]), lane) : 0u;
+            const unsigned rbar = (G > 1 && lane < G) ? map_to_rank(bar, lane) : 0u;
+            for (int j = 0; j < k; ++j) {
+                double x = (lane < nwarps) ? sh->warp_part[lane][j] : ident;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+                if (G == 1) {
+                    if (lane == 0) sh->inbox[half][0][j] = x;
+                } else if (lane < G) {
+                    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                                 :: "r"(slot0 + 8u * (unsigned)j), "l"(__double_as_longlong(x)), "r"(rbar) : "memory");
+                }
+            }
+        }
+#else
+        const unsigned bar = smem_u32(&sh->mbar[half]);
         if (tid < G * k) {
             const int dst = tid / k, j = tid - dst * k;
             double s = sh->warp_part[0][j];
             for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][j]);
-            double* slot = &sh->inbox[parity][rank][j];
-            if (G > 1) slot = cg::this_cluster().map_shared_rank(slot, dst);
-            *slot = s;
+            if (G == 1) {
+                sh->inbox[half][0][j] = s;
+            } else {
+                const unsigned slot = map_to_rank(smem_u32(&sh->inbox[half][rank][j]), dst);
+                const unsigned rbar = map_to_rank(bar, dst);
+                asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                             :: "r"(slot), "l"(__double_as_longlong(s)), "r"(rbar) : "memory");
+            }
         }
-        cluster_sync();
+#endif
+        if (G == 1) {
+            __syncthreads();
+        } else {
+            if (tid == 0) {
+                unsigned long long state;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;"
+                             : "=l"(state) : "r"(bar), "r"((unsigned)(G * k * 8)) : "memory");
+                (void)state;
+            }
+            const unsigned ph = (parity >> (1 + half)) & 1;
+            unsigned done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+            }
+            parity ^= 2 << half;
+        }
         for (int j = 0; j < k; ++j) {
-            double s = sh->inbox[parity][0][j];
-            for (int r = 1; r < G; ++r) s = red_combine(op, s, sh->inbox[parity][r][j]);
+            double s = sh->inbox[half][0][j];
+            for (int r = 1; r < G; ++r) s = red_combine(op, s, sh->inbox[half][r][j]);
             v[j] = s;
         }
         parity ^= 1;
@@ -80,11 +136,23 @@ struct DeviceCtx {
     __device__ __forceinline__ void allreduce_max(double& v) { allreduce(2, &v, 1); }
 };
 
+// every CTA initialises its two transaction barriers (one arrival each: its own expect_tx); the first
+// next_item() cluster barrier publishes them before any peer can target them
+__device__ __forceinline__ void init_ctx_barriers(const DeviceCtx& c) {
+    if (c.tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&c.sh->mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&c.sh->mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
     DeviceCtx c;
     c.tid = threadIdx.x; c.nt = blockDim.x; c.G = G;
     c.rank = (G > 1) ? (int)cg::this_cluster().block_rank() : 0;
     c.sh = sh; c.parity = 0;
+    init_ctx_barriers(c);
     return c;
 }
 

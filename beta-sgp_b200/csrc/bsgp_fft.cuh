@@ -97,73 +97,77 @@ template <int LOG2R, bool INV, typename T> BSGP_DEV void dft_r(cplx<T>* v) {
 // inverse:  V[q] = in[q] * conj(W_L^(q j));  out = IDFT_R(V)          (unnormalised)
 // tw[] holds W_n^k, k in [0, n); W_L^(q j) = tw[q j (n / L)].
 // ---------------------------------------------------------------------------------------------
+// Addressing.  With the padding period 2^ps and every non-final stage stride S a multiple of it
+// (make_fft_plan guarantees this), the R elements of a task sit at a CONSTANT padded stride:
+//   fpad(p0 + r S) = fpad(p0) + r (S + S / 2^ps)      (S >= 2^ps),      fpad(p0 + r) = fpad(p0) + r   (final stage),
+// so one base address per task replaces two shifts and two adds per element.
 template <int LOG2R, bool INV, typename T>
-BSGP_DEV void stage_task(cplx<T>* a, int ps, int lgL, int blk, int j, const cplx<T>* tw, int lg_twstep) {
+BSGP_DEV void stage_task(cplx<T>* a, int spad, bool twiddle, int j, const cplx<T>* tw, int lg_twstep) {
     constexpr int R = 1 << LOG2R;
-    const int lgS = lgL - LOG2R;
-    const int p0 = (blk << lgL) + j;
     cplx<T> v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = a[fpad(p0 + (r << lgS), ps)];
+    for (int r = 0; r < R; ++r) v[r] = a[r * spad];
     if (!INV) {
         dft_r<LOG2R, false>(v);
-        if (lgS > 0) {
+        if (twiddle) {
 #pragma unroll
             for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tw[(q * j) << lg_twstep]);
         }
     } else {
-        if (lgS > 0) {
+        if (twiddle) {
 #pragma unroll
             for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], tw[(q * j) << lg_twstep]);
         }
         dft_r<LOG2R, true>(v);
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[fpad(p0 + (r << lgS), ps)] = v[r];
+    for (int r = 0; r < R; ++r) a[r * spad] = v[r];
 }
 
 template <int LOG2R, bool INV, class Ctx, typename T>
-BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, int lgL, const cplx<T>* tw) {
-    const int lg_per = pl.log2n - LOG2R;          // butterflies per transform
+BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, int log2n, int ps, int lgL, const cplx<T>* tw) {
+    const int lg_per = log2n - LOG2R;             // butterflies per transform
     const int lgS = lgL - LOG2R;
     const int total = nfft << lg_per;
-    const int ps = pl.pad_shift, lg_tw = pl.log2n - lgL;
+    const int lg_tw = log2n - lgL;
+    const int S = 1 << lgS;
+    const int spad = (lgS >= ps) ? S + (S >> ps) : S;
     for (int t = ctx.tid; t < total; t += ctx.nt) {
         const int f = t >> lg_per, u = t & ((1 << lg_per) - 1);
-        stage_task<LOG2R, INV>(ws + f * fstride, ps, lgL, u >> lgS, u & ((1 << lgS) - 1), tw, lg_tw);
+        const int j = u & (S - 1);
+        const int p0 = ((u >> lgS) << lgL) + j;
+        stage_task<LOG2R, INV>(ws + f * fstride + p0 + (p0 >> ps), spad, lgS > 0, j, tw, lg_tw);
     }
     ctx.sync();
 }
 
 template <bool INV, class Ctx, typename T>
-BSGP_DEV void dispatch_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, int lg_r, int lgL,
-                             const cplx<T>* tw) {
-    switch (lg_r) {
-        case 1: run_stage<1, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
-        case 2: run_stage<2, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
-        default: run_stage<3, INV>(ctx, ws, nfft, fstride, pl, lgL, tw); break;
+BSGP_DEV void run_stages(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+    const int log2n = pl.log2n, ps = pl.pad_shift, ns = pl.nstages;
+    int lgL = INV ? 0 : log2n;
+    for (int i = 0; i < ns; ++i) {
+        const int lg_r = pl.log2r[INV ? ns - 1 - i : i];
+        if (INV) lgL += lg_r;
+        switch (lg_r) {
+            case 1: run_stage<1, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+            case 2: run_stage<2, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+            default: run_stage<3, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+        }
+        if (!INV) lgL -= lg_r;
     }
 }
 
+constexpr unsigned kNoSmem = 0xffffffffu;
+
 // nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout), ws = shared memory at byte
-// offset ws_off.  Ends with a barrier.
+// offset ws_off; twiddles at shared-memory offset tw_off, or through the generic pointer tw when tw_off == kNoSmem.
+// Ends with a barrier.
 // Not inlined: the solver runs five convolutions, all sharing one copy of each direction.
 template <bool INV, class Ctx, typename T>
-BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
-    if (!INV) {
-        int lgL = pl.log2n;
-        for (int s = 0; s < pl.nstages; ++s) {
-            dispatch_stage<false>(ctx, ws, nfft, fstride, pl, pl.log2r[s], lgL, tw);
-            lgL -= pl.log2r[s];
-        }
-    } else {
-        int lgL = 0;
-        for (int s = pl.nstages - 1; s >= 0; --s) {
-            lgL += pl.log2r[s];
-            dispatch_stage<true>(ctx, ws, nfft, fstride, pl, pl.log2r[s], lgL, tw);
-        }
-    }
+    if (tw_off != kNoSmem) run_stages<INV>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));   // twiddles in shared memory
+    else run_stages<INV>(ctx, ws, nfft, fstride, pl, tw);
 }
 
 }  // namespace bsgp

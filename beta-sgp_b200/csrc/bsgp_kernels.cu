@@ -16,6 +16,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -71,9 +72,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             };
             auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, off_ppx, spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
             T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
             const T* s0 = src + (size_t)r0 * nx;
@@ -82,11 +83,11 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
             auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, off_ppx, spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
-            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, off_ppx, spec, cf, ca);
+            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -211,15 +212,33 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
         G = 1;
         while (G < 8 && npix * sizeof(T) / G > 65536 && p->ny % (4 * G) == 0 && (p->nx / 2) % (2 * G) == 0) G *= 2;
     }
-    int threads = p->want_threads;
+    // Threads and CTAs per SM.  The solve is a chain of short phases separated by reductions, so one CTA leaves
+    // the SM idle while it waits; several small CTAs of DIFFERENT images per SM fill those gaps (measured on
+    // B200, 320 solves of 256x256: 1 x 512 threads 112 ms, 2 x 256 threads 94 ms, 4 x 128 threads 87 ms).
+    //   big slabs   : 4 CTAs x 128 threads, 38 KB FFT workspace, per-image state in L2 / HBM
+    //   small slabs : (stamps) 2 CTAs x 256 threads, everything resident in shared memory
     const size_t nslab = npix / G;
-    if (threads <= 0) threads = (nslab <= 2048) ? 256 : 512;
+    const bool small_slab = nslab * sizeof(T) <= 16384;
+    int threads = p->want_threads;
+    if (threads <= 0) threads = small_slab ? 256 : 128;
     if (threads != 256 && threads != 512 && threads != 128) return fail(BSGP_E_ARG, "threads must be 128, 256 or 512");
-    const size_t ws_limit = 76 * 1024;
-    if (!make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes))
-        return fail(BSGP_E_SHAPE, "unsupported shape %dx%d for cluster size %d (power-of-two sides >= 16 required)", p->ny, p->nx, G);
+    int minb = threads >= 512 ? 1 : (threads >= 256 ? (small_slab ? 2 : 1) : (small_slab ? 3 : 4));
+    if (const char* e = getenv("BSGP_MINB")) {             // tuning experiments: CTAs per SM
+        const int v = atoi(e);
+        if (threads == 256 && (v == 1 || v == 2)) minb = v;
+        if (threads == 128 && (v == 3 || v == 4)) minb = v;
+    }
+    size_t ws_limit = (minb >= 4 ? 38 : 76) * 1024;
+    if (const char* e = getenv("BSGP_WS_KB")) { const int v = atoi(e); if (v >= 8 && v <= 200) ws_limit = (size_t)v * 1024; }
+    bool ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes);
+    if (!ok && p->want_threads <= 0) {
+        // one transform does not fit the small workspace (sides >= 4096): fall back to one big CTA per SM
+        threads = 512; minb = 1; ws_limit = 160 * 1024;
+        ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes);
+    }
+    if (!ok) return fail(BSGP_E_SHAPE, "unsupported shape %dx%d for cluster size %d (power-of-two sides >= 16 required)", p->ny, p->nx, G);
     p->threads = threads;
-    p->minb = threads >= 512 ? 1 : (threads >= 256 ? (nslab * sizeof(T) > 16384 ? 1 : 2) : 3);
+    p->minb = minb;
     // shared-memory layout: [SharedCtl][ImgState][twiddles][position table][workspace][resident slabs]
     SmemPlan sp;
     size_t off = up128(sizeof(SharedCtl));
@@ -337,7 +356,7 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     memset(&a, 0, sizeof a);
     a.p = *prm; a.g = p->g; a.batch = batch;
     a.gn = (const T*)in->gn; a.bkg = (const T*)in->bkg; a.bkg_is_image = in->bkg_is_image; a.flux = in->flux; a.beta0 = in->beta0;
-    a.x0 = (const T*)in->x0; a.obj = (const T*)in->obj;
+    a.x0 = (const T*)in->x0; a.obj = (const T*)in->obj; a.order = in->order;
     a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = p->n_psf;
     a.work = (T*)p->work; a.work_stride = p->work_stride; a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride;
     a.resident_mask = p->resident_mask;
@@ -494,19 +513,20 @@ int bsgp_solve_batch_host(bsgp_plan* p, const bsgp_params* prm, int batch, const
     if (!p || !prm || !in || !out) return fail(BSGP_E_ARG, "NULL argument");
     CU(cudaSetDevice(p->device));
     const size_t img = (size_t)p->ny * p->nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
-    DevBuf gn, bkg, flux, beta0, x0, obj, x, iters, status, discr, times, stopv, err, bfin, pe, lt, sc, ta, tl, tb, tt, te;
+    DevBuf gn, bkg, flux, beta0, x0, obj, order, x, iters, status, discr, times, stopv, err, bfin, pe, lt, sc, ta, tl, tb, tt, te;
     int rc;
 #define TRY(e) do { rc = (e); if (rc) return rc; } while (0)
     TRY(gn.up(in->gn, B * img));
     TRY(bkg.up(in->bkg, in->bkg_is_image ? B * img : B * p->elem));
     TRY(flux.up(in->flux, B * 8)); TRY(beta0.up(in->beta0, B * 8)); TRY(x0.up(in->x0, B * img)); TRY(obj.up(in->obj, B * img));
+    TRY(order.up(in->order, B * 4));
     TRY(x.alloc(true, B * img)); TRY(iters.alloc(true, B * 4)); TRY(status.alloc(true, B * 4));
     TRY(discr.alloc(true, B * tr * 8)); TRY(times.alloc(true, B * tr * 8));
     TRY(stopv.alloc(out->stop_value, B * tr * 8)); TRY(err.alloc(out->err, B * (tr + 1) * 8)); TRY(bfin.alloc(out->beta_final, B * 8));
     TRY(pe.alloc(out->proj_evals, B * 4)); TRY(lt.alloc(out->ls_trials, B * 4)); TRY(sc.alloc(out->scalars, B * BSGP_NSCALARS * 8));
     TRY(ta.alloc(out->trace_alpha, B * tr * 8)); TRY(tl.alloc(out->trace_lambda, B * tr * 8)); TRY(tb.alloc(out->trace_beta, B * tr * 8));
     TRY(tt.alloc(out->trace_trials, B * tr * 4)); TRY(te.alloc(out->trace_evals, B * tr * 4));
-    bsgp_inputs di = {gn.d, bkg.d, in->bkg_is_image, (const double*)flux.d, (const double*)beta0.d, x0.d, obj.d};
+    bsgp_inputs di = {gn.d, bkg.d, in->bkg_is_image, (const double*)flux.d, (const double*)beta0.d, x0.d, obj.d, (const int*)order.d};
     bsgp_outputs dout = {x.d, (int*)iters.d, (int*)status.d, (double*)discr.d, (double*)times.d, (double*)stopv.d, (double*)err.d,
                          (double*)bfin.d, (int*)pe.d, (int*)lt.d, (double*)sc.d, (double*)ta.d, (double*)tl.d, (double*)tb.d,
                          (int*)tt.d, (int*)te.d};

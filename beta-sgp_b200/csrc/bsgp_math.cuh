@@ -97,7 +97,21 @@ BSGP_DEV double mrint(double a) { return rint(a); }
 static __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 #endif
 
+// polynomial coefficients live in constant memory: the fp64 pipe reads them as c[bank][offset] operands, whereas
+// immediates would each cost two uniform-register moves per use
+#define BSGP_LOG_COEFFS {2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0}
+#define BSGP_EXP_COEFFS {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, \
+                         1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5}
+#if !defined(BSGP_HOST_EMUL) && defined(BSGP_OPT_CONSTMEM)
+static __constant__ double kLogC[11] = BSGP_LOG_COEFFS;
+static __constant__ double kExpC[12] = BSGP_EXP_COEFFS;
+#define BSGP_POW_TABLES
+#else
+#define BSGP_POW_TABLES constexpr double kLogC[11] = BSGP_LOG_COEFFS; constexpr double kExpC[12] = BSGP_EXP_COEFFS;
+#endif
+
 BSGP_DEV double pow_inline(double x, double y) {
+    BSGP_POW_TABLES
     if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return pow_slow(x, y);
     // ---- log(x) = (lh, ll)
     int hx = hi_word(x);
@@ -115,17 +129,9 @@ BSGP_DEV double pow_inline(double x, double y) {
     const double ql = rem * r;                                     // q = qh + ql = f / (m + 1)
     const double q2 = qh * qh;
     // 2 atanh(q) - 2q = 2 q^3 (1/3 + q^2/5 + ... + q^20/23)
-    double p = 2.0 / 23.0;
-    p = mfma(p, q2, 2.0 / 21.0);
-    p = mfma(p, q2, 2.0 / 19.0);
-    p = mfma(p, q2, 2.0 / 17.0);
-    p = mfma(p, q2, 2.0 / 15.0);
-    p = mfma(p, q2, 2.0 / 13.0);
-    p = mfma(p, q2, 2.0 / 11.0);
-    p = mfma(p, q2, 2.0 / 9.0);
-    p = mfma(p, q2, 2.0 / 7.0);
-    p = mfma(p, q2, 2.0 / 5.0);
-    p = mfma(p, q2, 2.0 / 3.0);
+    double p = kLogC[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = mfma(p, q2, kLogC[i]);
     const double tail = (p * q2) * qh;
     const double ed = (double)e;
     const double a = ed * 6.93147180369123816490e-01;              // exact: ln2_hi has 21 trailing zero bits
@@ -145,18 +151,9 @@ BSGP_DEV double pow_inline(double x, double y) {
     double rr = mfma(-n, 6.93147180559945286227e-01, th);
     rr = mfma(-n, 2.31904681384629955842e-17, rr) + tl;
     // exp(rr) = 1 + (rr + rr^2 (1/2 + rr/6 + ... + rr^11/13!)); the last addition carries the only 1/2-ulp rounding
-    double z = 1.0 / 6227020800.0;
-    z = mfma(z, rr, 1.0 / 479001600.0);
-    z = mfma(z, rr, 1.0 / 39916800.0);
-    z = mfma(z, rr, 1.0 / 3628800.0);
-    z = mfma(z, rr, 1.0 / 362880.0);
-    z = mfma(z, rr, 1.0 / 40320.0);
-    z = mfma(z, rr, 1.0 / 5040.0);
-    z = mfma(z, rr, 1.0 / 720.0);
-    z = mfma(z, rr, 1.0 / 120.0);
-    z = mfma(z, rr, 1.0 / 24.0);
-    z = mfma(z, rr, 1.0 / 6.0);
-    z = mfma(z, rr, 0.5);
+    double z = kExpC[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) z = mfma(z, rr, kExpC[i]);
     double sm = mfma(z * rr, rr, rr);                              // exp(rr) - 1
     z = 1.0 + sm;
     return bits_hi_lo(hi_word(z) + ((int)n << 20), lo_word(z));

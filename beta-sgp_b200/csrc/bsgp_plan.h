@@ -40,6 +40,12 @@ inline bool make_fft_plan(int n, FftPlan* pl) {
     pl->nstages = ns;
     pl->pad_shift = pl->log2r[ns - 1];
     pl->plen = n + (n >> pl->pad_shift);
+    // run_stage's constant-stride addressing needs every non-final stage stride to be a multiple of the padding period
+    int lgL = pl->log2n;
+    for (int s = 0; s + 1 < ns; ++s) {
+        lgL -= pl->log2r[s];
+        if (lgL < pl->pad_shift) return false;
+    }
     return true;
 }
 

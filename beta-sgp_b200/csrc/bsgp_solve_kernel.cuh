@@ -37,21 +37,23 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
         S->ppx_off = sp.off_ppx;
         S->ws_off = sp.off_ws;
         S->spec = a.spec + (size_t)cluster_id * a.spec_stride;
-        S->twx = sp.tw_smem ? twx_s : a.twx;
-        S->twy = sp.tw_smem ? twy_s : a.twy;
+        S->twx = a.twx; S->twy = a.twy;
+        S->twx_off = sp.tw_smem ? sp.off_twx : kNoSmem;
+        S->twy_off = sp.tw_smem ? sp.off_twy : kNoSmem;
     }
     __syncthreads();
     for (;;) {
-        const int img = next_item(ctx, a.queue);
-        if (img >= a.batch) break;
+        const int item = next_item(ctx, a.queue);
+        if (item >= a.batch) break;
+        const int img = a.order ? a.order[item] : item;
         cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
         solve_image<T>(ctx, a, S, buf, tf, img);
     }
 }
 
-// register budgets: 512 x 128, 256 x 255 (one CTA per SM: big slabs), 256 x 128 (two CTAs per SM), 128 x 168 (three)
+// register budgets: 512 x 128, 256 x 255 (one CTA per SM), 256 x 128 (two CTAs per SM), 128 x 168 (three), 128 x 128 (four)
 template <typename T> static const void* solve_kernel_ptr(int threads, int minb) {
-    if (threads <= 128) return (const void*)bsgp_solve_kernel<T, 128, 3>;
+    if (threads <= 128) return minb >= 4 ? (const void*)bsgp_solve_kernel<T, 128, 4> : (const void*)bsgp_solve_kernel<T, 128, 3>;
     if (threads <= 256) return minb >= 2 ? (const void*)bsgp_solve_kernel<T, 256, 2> : (const void*)bsgp_solve_kernel<T, 256, 1>;
     return (const void*)bsgp_solve_kernel<T, 512, 1>;
 }

@@ -29,6 +29,12 @@
 #include "bsgp_conv.cuh"
 #include "bsgp_project.cuh"
 
+#ifdef BSGP_OPT_KSUM2
+#define BSGP_ACY acy
+#else
+#define BSGP_ACY acc
+#endif
+
 namespace bsgp {
 
 enum Buf { B_GN = 0, B_BKG, B_X, B_G, B_XTF, B_D, B_DTF, B_T1, NBUF };
@@ -39,7 +45,7 @@ template <typename T> struct SolveArgs {
     ConvGeom g;
     int batch;
     // inputs
-    const T* gn; const T* bkg; int bkg_is_image; const double* flux; const double* beta0; const T* x0; const T* obj;
+    const T* gn; const T* bkg; int bkg_is_image; const double* flux; const double* beta0; const T* x0; const T* obj; const int* order;
     // tables
     const cplx<T>* twx; const cplx<T>* twy; cplx<T>* tf; int n_psf;
     // per-cluster global scratch
@@ -58,6 +64,7 @@ template <typename T> struct ImgState {
     const T* gn_raw; const T* bkg_raw; const T* x0_raw; const T* truth; T* x_out;
     const cplx<T>* twx; const cplx<T>* twy; cplx<T>* spec; cplx<T>* tf;
     unsigned ws_off, ppx_off;        // FFT workspace and position table: byte offsets into dynamic shared memory
+    unsigned twx_off, twy_off;       // twiddle tables in shared memory, or kNoSmem (then twx / twy are used)
     ConvGeom geom;
     int nslab, bkg_img, init_recon, has_cap, pflag, want_err, stop2;
     T bkg_raw_s, scaling, bkg_s, null_fill, x_const, cap, xlo, xhi;
@@ -287,25 +294,25 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
     const T* src = which ? S->gn : S->x;
     auto pf = [&](int i) { In1<T> r; r.a = ld2(src, i); return r; };
     auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
 template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3];
-    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
+    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
     auto cf = [&](int i) { In2<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
         st2(xtf, i, v);
         V2<T> p;
         p.x = objective_pixel(dk, in.a.x, nadd(v.x, in.b.x), v.x, want_s1 != 0, acc);
-        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, acc);
+        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, BSGP_ACY);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
-    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
     return r;
 }
 
@@ -325,7 +332,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx, const Im
         if (kind == 0) return in.c;
         return mk2(nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))), nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))));
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer: g = 1 - w (KL) or den^(beta-1) - w                            sgp.py:262 / 705
@@ -335,7 +342,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx, const I
     auto ca = [&](int i, const In1<T>& in, V2<T> w) {
         st2(gr, i, (kind == 0) ? mk2(nsub((T)1, w.x), nsub((T)1, w.y)) : mk2(nsub(in.a.x, w.x), nsub(in.a.y, w.y)));
     };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
 }
 
 // consumer: bounds of the scaling matrix from y = flux/(flux+bkg) * A^T(gn)     sgp.py:268-270 / 712-714
@@ -350,7 +357,7 @@ template <typename T, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const Im
         if (yv > hi) hi = yv;
     };
     auto ca = [&](int, const In1<T>& in, V2<T> w) { one(in.a.x, w.x); one(in.a.y, w.y); };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
     R2 r; r.a = lo; r.b = hi;
     return r;
 }
@@ -419,7 +426,7 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
         st2(dbuf, i, d);
         return d;
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
     return gd;
 }
 
@@ -427,8 +434,8 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
 template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3];
-    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
+    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
     auto cf = [&](int i) { In3<T> r; r.a = ld2(xtf, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.c = ld2(gn, i); return r; };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
         st2(dtf, i, v);
@@ -436,11 +443,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const Img
         const T xt0 = nadd(in.a.x, v.x);                   // lam = 1
         p.x = objective_pixel(dk, in.c.x, nadd(xt0, in.b.x), xt0, want_s1 != 0, acc);
         const T xt1 = nadd(in.a.y, v.y);
-        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, acc);
+        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, BSGP_ACY);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
-    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
     return r;
 }
 
@@ -466,8 +473,8 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgSta
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3];
-    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
+    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
     auto fetch = [&](int i) {
         In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
     };
@@ -476,11 +483,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgSta
         const T xt0 = nadd(in.a.x, nmul(lam, in.b.x));
         p.x = objective_pixel(dk, in.d.x, nadd(xt0, in.c.x), xt0, want_s1 != 0, acc);
         const T xt1 = nadd(in.a.y, nmul(lam, in.b.y));
-        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, acc);
+        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, BSGP_ACY);
         st2(t1, i, p);
     };
     pair_loop<2>(ctx, S->nslab, fetch, body);
-    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
+    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
     return r;
 }
 
@@ -518,7 +525,7 @@ template <typename T, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgSta
         gnew.y = one(in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
         st2(gr, i, gnew);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
     R7 r;
 #pragma unroll
     for (int k = 0; k < 7; ++k) r.v[k] = bb[k];
@@ -537,7 +544,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_store_out(Ctx ctx, const 
 // the two column passes between a producer and a consumer
 template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgState<T>* S, cplx<T>* tf, int mode) {
     ctx.cluster_sync();
-    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->spec, tf, mode);
+    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->twy_off, S->spec, tf, mode);
     ctx.cluster_sync();
 }
 

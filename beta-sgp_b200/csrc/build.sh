@@ -5,14 +5,16 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $BSGP_NVCC_FLAGS"
-mkdir -p build
+OUT=${BSGP_OUT:-libbsgp.so}
+B=build${BSGP_TAG:+_$BSGP_TAG}
+mkdir -p $B
 pids=()
 for tu in bsgp_kernels bsgp_solve_f64 bsgp_solve_f32; do
-    $NVCC $FLAGS -c -o build/$tu.o $tu.cu > build/$tu.log 2>&1 &
+    $NVCC $FLAGS -c -o $B/$tu.o $tu.cu > $B/$tu.log 2>&1 &
     pids+=($!)
 done
 rc=0
 for pid in "${pids[@]}"; do wait $pid || rc=1; done
-cat build/*.log
+cat $B/*.log
 [ $rc -eq 0 ] || exit 1
-$NVCC -shared -o libbsgp.so build/bsgp_kernels.o build/bsgp_solve_f64.o build/bsgp_solve_f32.o
+$NVCC -shared -o $OUT $B/bsgp_kernels.o $B/bsgp_solve_f64.o $B/bsgp_solve_f32.o

@@ -127,6 +127,16 @@ class BatchResult:
     trace: dict | None = None
 
 
+def _queue_order(divergence, beta0):
+    """Order in which the persistent clusters pull images from the work queue.  Iteration counts of beta-SGP
+    grow as beta approaches 1 (28..162 iterations over the reference's five beta initialisations,
+    application_sgp_subdivisions.py:69-107), so the images with the smallest |beta - 1| go first: the long
+    solves do not end up alone at the tail of the queue.  Results do not depend on the order."""
+    if divergence != "beta" or beta0.size < 2 or np.all(beta0 == beta0[0]):
+        return None
+    return np.ascontiguousarray(np.argsort(np.abs(beta0 - 1.0), kind="stable").astype(np.int32))
+
+
 def _params(divergence, kw, has_flux):
     unknown = set(kw) - set(_SOLVER_KEYS)
     if unknown:
@@ -183,7 +193,8 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
     def ptr(a):
         return None if a is None else a.ctypes.data
 
-    ci = _capi.Inputs(ptr(gn), ptr(bkg_a), bkg_img, ptr(fl), ptr(b0), ptr(x0a), ptr(obja))
+    order = _queue_order(divergence, b0)
+    ci = _capi.Inputs(ptr(gn), ptr(bkg_a), bkg_img, ptr(fl), ptr(b0), ptr(x0a), ptr(obja), ptr(order))
     co = _capi.Outputs(ptr(out["x"]), ptr(out["iters"]), ptr(out["status"]), ptr(out["discr"]), ptr(out["times"]),
                        ptr(out["stop_value"]), ptr(out["err"]), ptr(out["beta_final"]), ptr(out["proj_evals"]),
                        ptr(out["ls_trials"]), ptr(out["scalars"]),
@@ -233,7 +244,11 @@ def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trac
         def ptr(t):
             return None if t is None else t.data_ptr()
 
-        ci = _capi.Inputs(ptr(gn), ptr(bkg_t), bkg_img, ptr(fl), ptr(b0), ptr(x0t), ptr(objt))
+        order = None
+        if divergence == "beta" and B > 1:
+            # longest expected solve first (see _queue_order); computed on the device, no host sync
+            order = torch.argsort((b0 - 1.0).abs(), stable=True).to(torch.int32)
+        ci = _capi.Inputs(ptr(gn), ptr(bkg_t), bkg_img, ptr(fl), ptr(b0), ptr(x0t), ptr(objt), ptr(order))
         co = _capi.Outputs(ptr(out["x"]), ptr(out["iters"]), ptr(out["status"]), ptr(out["discr"]), ptr(out["times"]),
                            ptr(out["stop_value"]), ptr(out["err"]), ptr(out["beta_final"]), ptr(out["proj_evals"]),
                            ptr(out["ls_trials"]), ptr(out["scalars"]),
@@ -241,7 +256,7 @@ def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trac
                            ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
         check(lib().bsgp_solve_batch(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co), _stream_ptr()))
         res = BatchResult(trace=tr, **out)
-        res._keepalive = (gn, bkg_t, fl, b0, x0t, objt)
+        res._keepalive = (gn, bkg_t, fl, b0, x0t, objt, order)
     return res
 
 

@@ -73,6 +73,9 @@ typedef struct bsgp_inputs {
     const double* beta0;   /* [batch] initial betaParam (BSGP_DIV_BETA) or NULL */
     const void* x0;        /* [batch][ny][nx] start images for init_recon = 1, else NULL */
     const void* obj;       /* [batch][ny][nx] ground truth for errflag, else NULL */
+    const int* order;      /* [batch] permutation: the work queue hands out image order[0], order[1], ... (longest expected
+                              solve first keeps the tail of the queue short); NULL = 0, 1, 2, ...  Results are always
+                              stored at the image's own index. */
 } bsgp_inputs;
 
 #define BSGP_NSCALARS 8    /* scaling, flux (scaled), X_low_bound, X_upp_bound, tol, fv_final, alpha_final, tau_final */

@@ -56,8 +56,8 @@ template <typename T> struct HostPlan {
                     In1<T> q; q.a = ld2(psf + (size_t)((r0 + row + ny / 2) & (ny - 1)) * nx, (c + nx / 2) & (nx - 1)); return q;
                 };
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), pf, pe);
-                else conv_cols(ctx, &g, ws_off, twy.data(), spec.data(), tf.data(), CONV_MAKE_TF);
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), pf, pe);
+                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), tf.data(), CONV_MAKE_TF);
             }
     }
     void apply(const T* x, T* y, int adjoint) {
@@ -71,9 +71,9 @@ template <typename T> struct HostPlan {
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
                 auto cf = [&](int) { In1<T> q; q.a = mk2((T)0, (T)0); return q; };
                 auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(y + off, i, v); };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), pf, pe);
-                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
-                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), ppx_off, spec.data(), cf, ca);
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), pf, pe);
+                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
+                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), cf, ca);
             }
     }
 };
@@ -92,8 +92,8 @@ int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after
         for (int i = 0; i < n; ++i) ws[(size_t)f * stride + fpad(i, pl.pad_shift)] = cmake<double>(in[2 * ((size_t)f * n + i)], in[2 * ((size_t)f * n + i) + 1]);
     HostCtx ctx;
     g_emul_smem = reinterpret_cast<unsigned char*>(ws.data());
-    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data());
-    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data());
+    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), kNoSmem);
+    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), kNoSmem);
     for (int f = 0; f < nfft; ++f)
         for (int k = 0; k < n; ++k) {
             const int p = inverse_after ? k : pos_of_freq(pl, k);
@@ -146,7 +146,7 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     HostCtx ctx;
     ImgState<double> S;
     memset(&S, 0, sizeof(S));
-    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data();
+    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem;
     pl.bind();
     solve_image<double>(ctx, a, &S, buf, pl.tf.data(), 0);
     return 0;

@@ -2,7 +2,7 @@
 # One GPU session: parity tests, then benches (no profiler).  Usage: gpurun -- bash tools/gpu_round.sh [tag]
 tag=${1:-run}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$tag.log
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$tag.log
 tail -5 gpurun_out/pytest_gpu_$tag.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_tiles_$tag.json 2> gpurun_out/bench_tiles_$tag.err; echo "bench rc=$?"
 python bench.py --steps 3 --warmup 3 --workload stamps32 --no-cpu-baseline > gpurun_out/bench_stamps_$tag.json 2> gpurun_out/bench_stamps_$tag.err; echo "bench rc=$?"
