@@ -72,26 +72,6 @@ struct DeviceCtx {
             if (lane == 0) sh->warp_part[warp][j] = x;
         }
         __syncthreads();
-#ifdef BSGP_OPT_TREE
-        // warp 0 combines the per-warp partials with a fixed shuffle tree (same order in every CTA) and sends them
-        const unsigned bar = smem_u32(&sh->mbar[half]);
-        if (warp == 0) {
-            const double ident = (op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
-            const unsigned slot0 = (G > 1 && lane < G) ? map_to_rank(smem_u32(&sh->inbox[half][rank][0]), lane) : 0u;
-            const unsigned rbar = (G > 1 && lane < G) ? map_to_rank(bar, lane) : 0u;
-            for (int j = 0; j < k; ++j) {
-                double x = (lane < nwarps) ? sh->warp_part[lane][j] : ident;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
-                if (G == 1) {
-                    if (lane == 0) sh->inbox[half][0][j] = x;
-                } else if (lane < G) {
-                    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                                 :: "r"(slot0 + 8u * (unsigned)j), "l"(__double_as_longlong(x)), "r"(rbar) : "memory");
-                }
-            }
-        }
-#else
         const unsigned bar = smem_u32(&sh->mbar[half]);
         if (tid < G * k) {
             const int dst = tid / k, j = tid - dst * k;
@@ -106,7 +86,6 @@ struct DeviceCtx {
                              :: "r"(slot), "l"(__double_as_longlong(s)), "r"(rbar) : "memory");
             }
         }
-#endif
         if (G == 1) {
             __syncthreads();
         } else {

@@ -97,18 +97,12 @@ BSGP_DEV double mrint(double a) { return rint(a); }
 static __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 #endif
 
-// polynomial coefficients live in constant memory: the fp64 pipe reads them as c[bank][offset] operands, whereas
-// immediates would each cost two uniform-register moves per use
+// polynomial coefficients of pow_inline
 #define BSGP_LOG_COEFFS {2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0}
 #define BSGP_EXP_COEFFS {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, \
                          1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5}
-#if !defined(BSGP_HOST_EMUL) && defined(BSGP_OPT_CONSTMEM)
-static __constant__ double kLogC[11] = BSGP_LOG_COEFFS;
-static __constant__ double kExpC[12] = BSGP_EXP_COEFFS;
-#define BSGP_POW_TABLES
-#else
+// (as constexpr locals the coefficients become immediates; a __constant__ table measured 15 % slower)
 #define BSGP_POW_TABLES constexpr double kLogC[11] = BSGP_LOG_COEFFS; constexpr double kExpC[12] = BSGP_EXP_COEFFS;
-#endif
 
 BSGP_DEV double pow_inline(double x, double y) {
     BSGP_POW_TABLES

@@ -29,12 +29,6 @@
 #include "bsgp_conv.cuh"
 #include "bsgp_project.cuh"
 
-#ifdef BSGP_OPT_KSUM2
-#define BSGP_ACY acy
-#else
-#define BSGP_ACY acc
-#endif
-
 namespace bsgp {
 
 enum Buf { B_GN = 0, B_BKG, B_X, B_G, B_XTF, B_D, B_DTF, B_T1, NBUF };
@@ -301,18 +295,18 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
 template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
-    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto cf = [&](int i) { In2<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
         st2(xtf, i, v);
         V2<T> p;
         p.x = objective_pixel(dk, in.a.x, nadd(v.x, in.b.x), v.x, want_s1 != 0, acc);
-        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, BSGP_ACY);
+        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, acc);
         st2(t1, i, p);
     };
     conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
-    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
 
@@ -434,8 +428,8 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
 template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
-    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto cf = [&](int i) { In3<T> r; r.a = ld2(xtf, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.c = ld2(gn, i); return r; };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
         st2(dtf, i, v);
@@ -443,11 +437,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const Img
         const T xt0 = nadd(in.a.x, v.x);                   // lam = 1
         p.x = objective_pixel(dk, in.c.x, nadd(xt0, in.b.x), xt0, want_s1 != 0, acc);
         const T xt1 = nadd(in.a.y, v.y);
-        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, BSGP_ACY);
+        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, acc);
         st2(t1, i, p);
     };
     conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
-    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
 
@@ -473,8 +467,8 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgSta
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
-    KSum acc[3], acy[3];            // one compensated accumulator set per pixel of the pair: two independent dependency chains
-    acc[0].clear(); acc[1].clear(); acc[2].clear(); acy[0].clear(); acy[1].clear(); acy[2].clear();
+    KSum acc[3];
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto fetch = [&](int i) {
         In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
     };
@@ -483,11 +477,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgSta
         const T xt0 = nadd(in.a.x, nmul(lam, in.b.x));
         p.x = objective_pixel(dk, in.d.x, nadd(xt0, in.c.x), xt0, want_s1 != 0, acc);
         const T xt1 = nadd(in.a.y, nmul(lam, in.b.y));
-        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, BSGP_ACY);
+        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, acc);
         st2(t1, i, p);
     };
     pair_loop<2>(ctx, S->nslab, fetch, body);
-    R3 r; r.a = acc[0].value() + acy[0].value(); r.b = acc[1].value() + acy[1].value(); r.c = acc[2].value() + acy[2].value();
+    R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
 
