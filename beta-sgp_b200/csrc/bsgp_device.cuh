@@ -135,6 +135,67 @@ __device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
     return c;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Frame mode: ONE image spread over the whole GPU (sides >= 1024, BASELINE config 5: one 8192 x 8192
+// frame).  The same solver code runs with the grid in the role of the cluster: G = gridDim.x CTAs (a
+// power of two <= number of SMs, one per SM, cooperative launch), the "cluster barrier" is a grid
+// barrier, and the all-reduce goes through a small global buffer: every CTA publishes its k partials,
+// grid barrier, every CTA adds the G partials in the same order (warp j handles value j: strided sum
+// per lane in rank order, then a fixed shuffle tree), so all controllers agree bit for bit.
+// -------------------------------------------------------------------------------------------------
+struct GridCtx {
+    int tid, nt, rank, G;
+    SharedCtl* sh;
+    double* gpart;      // [2][G][kMaxK]
+    int parity;
+
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void cluster_sync() { cg::this_grid().sync(); }
+    __device__ __forceinline__ double now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return (double)t * 1e-9;
+    }
+    __device__ __forceinline__ void allreduce(int op, double* v, int k) {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+        const int half = parity & 1;
+        for (int j = 0; j < k; ++j) {
+            double x = v[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+            if (lane == 0) sh->warp_part[warp][j] = x;
+        }
+        __syncthreads();
+        if (tid < k) {
+            double s = sh->warp_part[0][tid];
+            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][tid]);
+            gpart[((size_t)half * G + rank) * kMaxK + tid] = s;
+        }
+        cg::this_grid().sync();
+        if (warp < k) {
+            const double ident = (op == 0) ? 0.0 : (op == 1 ? INFINITY : -INFINITY);
+            double x = ident;
+            for (int r = lane; r < G; r += 32) x = red_combine(op, x, __ldcg(&gpart[((size_t)half * G + r) * kMaxK + warp]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
+            if (lane == 0) sh->inbox[half][0][warp] = x;
+        }
+        __syncthreads();
+        for (int j = 0; j < k; ++j) v[j] = sh->inbox[half][0][j];
+        parity ^= 1;
+    }
+    __device__ __forceinline__ void allreduce_sum(double* v, int k) { allreduce(0, v, k); }
+    __device__ __forceinline__ void allreduce_min(double& v) { allreduce(1, &v, 1); }
+    __device__ __forceinline__ void allreduce_max(double& v) { allreduce(2, &v, 1); }
+};
+
+__device__ __forceinline__ GridCtx make_grid_ctx(SharedCtl* sh, double* gpart) {
+    GridCtx c;
+    c.tid = threadIdx.x; c.nt = blockDim.x; c.G = gridDim.x; c.rank = blockIdx.x;
+    c.sh = sh; c.gpart = gpart; c.parity = 0;
+    return c;
+}
+
 // next work item for the whole cluster (leader claims it, pushes it into every CTA's shared memory)
 __device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue) {
     if (ctx.rank == 0 && ctx.tid == 0) {

@@ -93,6 +93,52 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
     }
 }
 
+// Frame-mode twin of bsgp_conv_kernel: every item is processed by the whole (cooperative) grid.
+template <typename T>
+__global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<T> a, const unsigned off_geom, const unsigned off_ppx, const unsigned off_ws,
+                                                                 double* gpart) {
+    unsigned char* smem = dyn_smem();
+    GridCtx ctx = make_grid_ctx(reinterpret_cast<SharedCtl*>(smem), gpart);
+    ConvGeom* gs = reinterpret_cast<ConvGeom*>(smem + off_geom);
+    unsigned short* ppx = reinterpret_cast<unsigned short*>(smem + off_ppx);
+    if (ctx.tid == 0) *gs = a.g;
+    fill_pos_table(ctx, a.g.px, ppx);
+    __syncthreads();
+    const ConvGeom& g = *gs;
+    const int ny = a.g.ny, nx = a.g.nx;
+    const size_t npix = (size_t)ny * nx;
+    const int r0 = ctx.rank * a.g.rows_per_cta;
+    for (int img = 0; img < a.count; ++img) {
+        const T* src = a.in + (size_t)img * npix;
+        if (a.mode == CONV_MAKE_TF) {
+            const int lg_nx = a.g.lg_nx;
+            auto pf = [&](int i) {
+                const int row = i >> lg_nx, c = i & (nx - 1);
+                In1<T> r; r.a = ld2(src + (size_t)((r0 + row + (ny >> 1)) & (ny - 1)) * nx, (c + (nx >> 1)) & (nx - 1)); return r;
+            };
+            auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+            ctx.sync();
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, pf, pe);
+            ctx.cluster_sync();
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, a.spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+        } else {
+            T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
+            const T* s0 = src + (size_t)r0 * nx;
+            auto pf = [&](int i) { In1<T> r; r.a = ld2(s0, i); return r; };
+            auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
+            auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
+            auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
+            ctx.sync();
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, pf, pe);
+            ctx.cluster_sync();
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            ctx.cluster_sync();
+            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, cf, ca);
+        }
+        ctx.cluster_sync();   // spec is reused by the next item
+    }
+}
+
 // projectDF (flux_conserve_proj.py:7-144): one CTA per problem, x = clamp((c + lambda) / dia).
 __global__ void __launch_bounds__(512, 1) bsgp_project_kernel(const double* __restrict__ b, const double* __restrict__ c,
                                                               const double* __restrict__ dia, int n, int batch, double cap, int has_cap,
@@ -186,14 +232,16 @@ struct bsgp_plan {
     void* work = nullptr; size_t work_stride = 0;
     void* spec = nullptr; size_t spec_stride = 0;
     int* queue = nullptr;
+    bool frame = false;          // one image over the whole grid (cooperative launch) instead of one per cluster
+    double* gpart = nullptr;     // frame mode: all-reduce partials [2][G][kMaxK]
     size_t workspace_bytes = 0;
 };
 
 template <typename T> static const void* conv_kernel_ptr() { return (const void*)bsgp_conv_kernel<T>; }
 
 static void plan_free_buffers(bsgp_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue);
-    p->twx = p->twy = p->tf = p->work = p->spec = nullptr; p->queue = nullptr;
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue); cudaFree(p->gpart);
+    p->twx = p->twy = p->tf = p->work = p->spec = nullptr; p->queue = nullptr; p->gpart = nullptr;
     p->tf_capacity = 0; p->n_psf = 0;
 }
 
@@ -203,9 +251,78 @@ static inline size_t up128(size_t v) { return (v + 127) & ~(size_t)127; }
 // the most touches per iteration; the background image last (unused when the background is a scalar).
 static const int kResidencyOrder[NBUF] = {B_D, B_T1, B_G, B_X, B_XTF, B_DTF, B_GN, B_BKG};
 
+template <typename T> static const void* conv_frame_kernel_ptr() { return (const void*)bsgp_conv_frame_kernel<T>; }
+
+template <typename T> static int alloc_tables(bsgp_plan* p) {
+    std::vector<cplx<T>> tw;
+    make_twiddles<T>(p->nx, tw);
+    CU(cudaMalloc(&p->twx, tw.size() * sizeof(cplx<T>)));
+    CU(cudaMemcpy(p->twx, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    make_twiddles<T>(p->ny, tw);
+    CU(cudaMalloc(&p->twy, tw.size() * sizeof(cplx<T>)));
+    CU(cudaMemcpy(p->twy, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    return BSGP_OK;
+}
+
+template <typename T> static int plan_setup_frame(bsgp_plan* p) {
+    const size_t npix = (size_t)p->ny * p->nx;
+    p->elem = sizeof(T);
+    int G = 1;
+    while (2 * G <= p->num_sms && p->ny % (4 * G) == 0 && (p->nx / 2) % (2 * G) == 0) G *= 2;
+    const size_t ws_limit = 160 * 1024;
+    if (!make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes))
+        return fail(BSGP_E_SHAPE, "unsupported shape %dx%d for frame mode (grid of %d CTAs)", p->ny, p->nx, G);
+    p->threads = 512; p->minb = 1; p->resident_mask = 0; p->num_clusters = 1; p->conv_clusters = 1;
+    SmemPlan sp;
+    size_t off = up128(sizeof(SharedCtl));
+    sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
+    const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
+    sp.tw_smem = tw_bytes <= 16384;
+    sp.off_twx = sp.off_twy = (unsigned)off;
+    if (sp.tw_smem) {
+        off = up128(off + (size_t)p->nx * sizeof(cplx<T>));
+        if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + (size_t)p->ny * sizeof(cplx<T>)); }
+    }
+    sp.off_ppx = (unsigned)off; off = up128(off + (size_t)p->nx * sizeof(unsigned short));
+    sp.off_ws = (unsigned)off; off = up128(off + p->ws_bytes);
+    sp.off_bufs = (unsigned)off;
+    p->sp = sp;
+    p->smem_bytes = off;
+    p->conv_off_geom = (unsigned)up128(sizeof(SharedCtl));
+    p->conv_off_ppx = (unsigned)up128(p->conv_off_geom + sizeof(ConvGeom));
+    p->conv_off_ws = (unsigned)up128(p->conv_off_ppx + (size_t)p->nx * sizeof(unsigned short));
+    p->conv_smem = p->conv_off_ws + up128(p->ws_bytes);
+    if (p->smem_bytes > (size_t)p->max_smem || p->conv_smem > (size_t)p->max_smem)
+        return fail(BSGP_E_SHAPE, "shape %dx%d needs %zu B of shared memory per CTA (limit %d)", p->ny, p->nx, p->smem_bytes, p->max_smem);
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    if (!coop) return fail(BSGP_E_CUDA, "device does not support cooperative launches (frame mode)");
+    LaunchCfg lc{G, 512, 1, p->smem_bytes, nullptr, 1};
+    int per_sm = 0;
+    cudaError_t e = query_frame_ctas<T>(lc, &per_sm);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    if (per_sm < 1) return fail(BSGP_E_CUDA, "frame kernel does not fit: %zu B shared memory", p->smem_bytes);
+    CU(cudaFuncSetAttribute(conv_frame_kernel_ptr<T>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->conv_smem));
+    int rc = alloc_tables<T>(p);
+    if (rc) return rc;
+    p->work_stride = NBUF * npix;
+    p->spec_stride = (size_t)p->ny * p->g.hx;
+    p->tf_stride = (size_t)(p->g.hx + 1) * p->ny;
+    CU(cudaMalloc(&p->work, p->work_stride * sizeof(T)));
+    CU(cudaMalloc(&p->spec, p->spec_stride * sizeof(cplx<T>)));
+    CU(cudaMalloc((void**)&p->queue, sizeof(int)));
+    CU(cudaMalloc((void**)&p->gpart, (size_t)2 * G * kMaxK * sizeof(double)));
+    p->workspace_bytes = p->work_stride * sizeof(T) + p->spec_stride * sizeof(cplx<T>);
+    p->configured = true;
+    return BSGP_OK;
+}
+
 template <typename T> static int plan_setup_t(bsgp_plan* p) {
     const size_t npix = (size_t)p->ny * p->nx;
     p->elem = sizeof(T);
+    // Frame mode (bsgp_device.cuh, GridCtx): images of a megapixel or more get the whole GPU each
+    p->frame = (p->want_G == -1) || (p->want_G == 0 && npix >= ((size_t)1 << 20));
+    if (p->frame) return plan_setup_frame<T>(p);
     // cluster size: slabs of <= 64 KB, at most 8 CTAs (portable cluster limit)
     int G = p->want_G;
     if (G <= 0) {
@@ -290,13 +407,7 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     if (nc <= 0) return fail(BSGP_E_CUDA, "convolution kernel does not fit: cluster %d, %zu B shared memory", G, p->conv_smem);
     p->conv_clusters = nc;
 
-    std::vector<cplx<T>> tw;
-    make_twiddles<T>(p->nx, tw);
-    CU(cudaMalloc(&p->twx, tw.size() * sizeof(cplx<T>)));
-    CU(cudaMemcpy(p->twx, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
-    make_twiddles<T>(p->ny, tw);
-    CU(cudaMalloc(&p->twy, tw.size() * sizeof(cplx<T>)));
-    CU(cudaMemcpy(p->twy, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    { int rc = alloc_tables<T>(p); if (rc) return rc; }
     const int nscratch = p->num_clusters > p->conv_clusters ? p->num_clusters : p->conv_clusters;
     p->work_stride = NBUF * npix;
     p->spec_stride = (size_t)p->ny * p->g.hx;
@@ -316,6 +427,14 @@ static int plan_setup(bsgp_plan* p) {
 }
 
 template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int count, cudaStream_t st) {
+    if (p->frame) {
+        unsigned og = p->conv_off_geom, op = p->conv_off_ppx, ow = p->conv_off_ws;
+        double* gp = p->gpart;
+        void* args[] = {&a, &og, &op, &ow, &gp};
+        cudaError_t e = cudaLaunchCooperativeKernel(conv_frame_kernel_ptr<T>(), dim3(p->g.G), dim3(512), args, p->conv_smem, st);
+        if (e != cudaSuccess) return fail(BSGP_E_CUDA, "convolution kernel launch failed: %s", cudaGetErrorString(e));
+        return BSGP_OK;
+    }
     CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
     const int nclu = count < p->conv_clusters ? count : p->conv_clusters;
     LaunchCfg lc{nclu * p->g.G, 512, p->g.G, p->conv_smem, st};
@@ -365,6 +484,12 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     a.ls_trials = out->ls_trials; a.scalars = out->scalars; a.tr_alpha = out->trace_alpha; a.tr_lambda = out->trace_lambda;
     a.tr_beta = out->trace_beta; a.tr_trials = out->trace_trials; a.tr_evals = out->trace_evals;
     a.queue = p->queue;
+    if (p->frame) {
+        LaunchCfg fc{p->g.G, 512, 1, p->smem_bytes, st, 1};
+        cudaError_t fe = launch_frame<T>(fc, a, p->sp, p->tf_stride, p->gpart);
+        if (fe != cudaSuccess) return fail(BSGP_E_CUDA, "frame kernel launch failed: %s", cudaGetErrorString(fe));
+        return BSGP_OK;
+    }
     CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
     const int nclu = batch < p->num_clusters ? batch : p->num_clusters;
     LaunchCfg lc{nclu * p->g.G, p->threads, p->g.G, p->smem_bytes, st, p->minb};
@@ -399,8 +524,8 @@ int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan) {
     if (!plan) return fail(BSGP_E_ARG, "plan is NULL");
     *plan = nullptr;
     if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "dtype must be BSGP_F64 or BSGP_F32");
-    if (!is_pow2(ny) || !is_pow2(nx) || ny < 16 || nx < 16 || ny > 4096 || nx > 4096)
-        return fail(BSGP_E_SHAPE, "unsupported image shape %dx%d: the cluster solver handles power-of-two sides in [16, 4096]", ny, nx);
+    if (!is_pow2(ny) || !is_pow2(nx) || ny < 16 || nx < 16 || ny > 8192 || nx > 8192)
+        return fail(BSGP_E_SHAPE, "unsupported image shape %dx%d: the cluster solver handles power-of-two sides in [16, 8192]", ny, nx);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(BSGP_E_CUDA, "device %d not available (%d CUDA devices)", device, ndev);

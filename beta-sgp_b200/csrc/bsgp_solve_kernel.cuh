@@ -51,6 +51,61 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
     }
 }
 
+// Frame mode (GridCtx): the images of the batch are restored one after the other, each by the whole grid.
+template <typename T>
+__global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride, double* gpart) {
+    unsigned char* smem = dyn_smem();
+    GridCtx ctx = make_grid_ctx(reinterpret_cast<SharedCtl*>(smem), gpart);
+    ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);
+    const size_t npix = (size_t)a.g.ny * a.g.nx;
+    const size_t nslab = (size_t)a.g.rows_per_cta * a.g.nx;
+    T* buf[NBUF];
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) buf[b] = a.work + (size_t)b * npix + (size_t)ctx.rank * nslab;
+    cplx<T>* twx_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twx);
+    cplx<T>* twy_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twy);
+    if (sp.tw_smem) {
+        for (int k = ctx.tid; k < a.g.nx; k += ctx.nt) twx_s[k] = a.twx[k];
+        if (sp.off_twy != sp.off_twx) for (int k = ctx.tid; k < a.g.ny; k += ctx.nt) twy_s[k] = a.twy[k];
+    }
+    fill_pos_table(ctx, a.g.px, reinterpret_cast<unsigned short*>(smem + sp.off_ppx));
+    if (ctx.tid == 0) {
+        S->geom = a.g;
+        S->ppx_off = sp.off_ppx;
+        S->ws_off = sp.off_ws;
+        S->spec = a.spec;
+        S->twx = a.twx; S->twy = a.twy;
+        S->twx_off = sp.tw_smem ? sp.off_twx : kNoSmem;
+        S->twy_off = sp.tw_smem ? sp.off_twy : kNoSmem;
+    }
+    __syncthreads();
+    for (int img = 0; img < a.batch; ++img) {
+        cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
+        solve_image<T>(ctx, a, S, buf, tf, img);
+        ctx.cluster_sync();          // the scratch arrays and the exchange buffer are reused by the next image
+    }
+}
+
+template <typename T>
+cudaError_t launch_frame(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride, double* gpart) {
+    SolveArgs<T> args = a;
+    SmemPlan plan = sp;
+    size_t tfs = tf_stride;
+    double* gp = gpart;
+    void* params[] = {&args, &plan, &tfs, &gp};
+    const void* fn = (const void*)bsgp_frame_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchCooperativeKernel(fn, dim3(lc.grid), dim3(lc.threads), params, lc.smem, lc.stream);
+}
+
+template <typename T> cudaError_t query_frame_ctas(const LaunchCfg& lc, int* per_sm) {
+    const void* fn = (const void*)bsgp_frame_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, lc.threads, lc.smem);
+}
+
 // register budgets: 512 x 128, 256 x 255 (one CTA per SM), 256 x 128 (two CTAs per SM), 128 x 168 (three), 128 x 128 (four)
 template <typename T> static const void* solve_kernel_ptr(int threads, int minb) {
     if (threads <= 128) return minb >= 4 ? (const void*)bsgp_solve_kernel<T, 128, 4> : (const void*)bsgp_solve_kernel<T, 128, 3>;

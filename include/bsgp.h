@@ -102,7 +102,7 @@ typedef struct bsgp_outputs {
 
 typedef struct bsgp_plan_info {
     int ny, nx, dtype, device;
-    int cluster_size;      /* CTAs cooperating on one image */
+    int cluster_size;      /* CTAs cooperating on one image (cluster size, or the grid size in frame mode) */
     int num_clusters;      /* images in flight */
     int threads;           /* threads per CTA */
     int smem_bytes;        /* dynamic shared memory per CTA */
@@ -115,7 +115,9 @@ typedef struct bsgp_plan_info {
 int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan);
 int bsgp_plan_destroy(bsgp_plan* plan);
 int bsgp_plan_get_info(const bsgp_plan* plan, bsgp_plan_info* info);
-/* Tuning knobs (0 = automatic): cluster size and threads per CTA.  Call before bsgp_set_psf. */
+/* Tuning knobs (0 = automatic): cluster size and threads per CTA.  Call before bsgp_set_psf.
+ * cluster_size = -1 selects frame mode (one image at a time over the whole GPU, cooperative launch), which is
+ * the automatic choice for images of 2^20 pixels or more; info.cluster_size then reports the grid size. */
 int bsgp_plan_configure(bsgp_plan* plan, int cluster_size, int threads);
 
 /* TF = fftn(fftshift(psf)) for n_psf PSFs of the image shape (sgp.py:109 / 571); n_psf is 1 (shared by

@@ -174,6 +174,11 @@ int emul_project(const double* c, const double* dia, int n, double b, double sat
 
 }  // extern "C"
 
+// pow_inline (bsgp_math.cuh): the call-free pow used by the beta-divergence phases
+extern "C" void emul_pow(const double* x, const double* y, double* out, long long n) {
+    for (long long i = 0; i < n; ++i) out[i] = pow_inline(x[i], y[i]);
+}
+
 extern "C" int emul_sizeof_params() { return (int)sizeof(bsgp_params); }
 extern "C" int emul_sizeof_inputs() { return (int)sizeof(bsgp_inputs); }
 extern "C" int emul_sizeof_outputs() { return (int)sizeof(bsgp_outputs); }

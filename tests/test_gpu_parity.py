@@ -290,3 +290,68 @@ def test_fp32_mode_tolerance(bs, get_case, golden):
         assert abs(float(r.x[0].sum()) - xr.sum()) <= 1e-4 * xr.sum()
         assert np.abs(r.x[0] - xr).max() <= 1e-4 * np.abs(xr).max() * 50    # 27 iterations of fp32 rounding
         print(name, "fp32 iterations", int(r.iters[0]), "fp64", int(golden[name + "/iters"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# frame mode: one image over the whole GPU (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ngc_kl_27", "ngc_beta_p1_stop3", "ngc_beta_adapt", "tile01", "stamp01"])
+def test_frame_mode_parity(bs, name, get_case, golden):
+    """The grid-wide variant of the solver (cooperative launch, grid barrier, all-reduce through global memory),
+    forced on golden cases that normally run in cluster mode: the same strict bar."""
+    gn = get_case(name)[0]
+    plan = bs.Plan(gn.shape[0], gn.shape[1], cluster_size=-1)
+    assert plan.info()["cluster_size"] >= 8 and plan.info()["num_clusters"] == 1
+    r = _run(bs, name, get_case, plan=plan)
+    it = int(golden[name + "/iters"])
+    assert int(r.status[0]) == 0 and int(r.iters[0]) == it
+    ref = golden[name + "/discr"]
+    assert np.abs(r.discr[0, :it + 1] - ref).max() <= 1e-10 * np.abs(ref).max()
+    xs = golden[name + "/x_sub"]
+    assert np.abs(r.x[0][::8, ::8] - xs).max() <= 1e-8 * np.abs(xs).max()
+    assert np.array_equal(r.trace["evals"][0, 1:it + 1], golden[name + "/proj_evals"])
+    plan.close()
+
+
+def test_frame_mode_megapixel_against_oracle(bs):
+    """1024 x 1024 synthetic crowded frame, 2-D background, flux projection: frame mode is the automatic choice
+    from 2^20 pixels; compared with the oracle over 6 iterations."""
+    from oracle import sgp_oracle as orc
+    f = bs.synth.single_frame(1024, seed=5)
+    kw = dict(bs.synth.TILE_KWARGS, stop_criterion=1, MAXIT=6)
+    r = bs.sgp_betaDiv_batch(f["gn"][None], f["psf"], f["bkg"][None], flux=[f["flux"]], betaParam=1.0248357, **kw)
+    assert bs.get_plan(1024, 1024).info()["num_clusters"] == 1          # frame mode
+    o = orc.solve(f["gn"], f["psf"], f["bkg"], divergence="beta", flux=np.float64(f["flux"]), betaParam=1.0248357, **kw)
+    assert int(r.iters[0]) == o.iters == 6 and int(r.status[0]) == 0
+    assert np.abs(r.discr[0, :7] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    assert np.abs(r.x[0] - o.x).max() <= 1e-8 * np.abs(o.x).max()
+    assert int(r.proj_evals[0]) == sum(o.trace.proj_evals) + o.trace.init_proj_evals
+
+
+def test_frame_mode_8192_properties(bs):
+    """BASELINE config 5 at full size: one 8192 x 8192 frame on one GPU, beta-SGP with the flux-conserving
+    projection.  Size-independent properties: the operator is linear and conserves the sum (the PSF is
+    normalised), the restored image is non-negative, conserves the flux to the projection's tolerance, and the
+    objective decreases."""
+    n = 8192
+    rng = np.random.default_rng(11)
+    psf = bs.synth.moffat_psf(n, n, 3.5)
+    truth = np.zeros((n, n))
+    k = 150_000
+    truth[rng.integers(0, n, k), rng.integers(0, n, k)] = 10.0 ** rng.uniform(3.0, 5.0, k)
+    plan = bs.get_plan(n, n)
+    assert plan.info()["num_clusters"] == 1 and plan.info()["cluster_size"] == 128
+    plan.set_psf(psf)
+    blurred = plan.apply_psf(truth)
+    assert abs(blurred.sum() - truth.sum()) <= 1e-9 * truth.sum()
+    assert np.abs(plan.apply_psf(2.0 * truth) - 2.0 * blurred).max() <= 1e-12 * blurred.max()
+    sky = 300.0
+    gn = rng.poisson(np.maximum(blurred, 0.0) + sky).astype(np.float64)
+    flux = float((gn - sky).sum())
+    kw = dict(bs.synth.TILE_KWARGS, stop_criterion=1, MAXIT=3)
+    r = bs.sgp_betaDiv_batch(gn[None], psf, np.float64(sky), flux=[flux], betaParam=1.0248357, **kw)
+    assert int(r.status[0]) == 0 and int(r.iters[0]) == 3
+    assert r.x.min() >= 0.0 and np.isfinite(r.x).all()
+    assert abs(r.x[0].sum() - flux) <= 1e-9 * flux
+    assert np.all(np.diff(r.discr[0, :4]) < 0)
+    bs.clear_plans()
