@@ -35,9 +35,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tiles256", choices=["tiles256", "stamps32"])
+    ap.add_argument("--workload", default="tiles256", choices=["tiles256", "stamps32", "frame"])
     ap.add_argument("--field", type=int, default=2048, help="side of the synthetic field (tiles256)")
     ap.add_argument("--stamps", type=int, default=8192, help="number of stamps (stamps32)")
+    ap.add_argument("--frame", type=int, default=8192, help="side of the single frame (workload frame, BASELINE config 5)")
+    ap.add_argument("--maxit", type=int, default=10, help="iterations of the frame workload (stop_criterion=1)")
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -57,6 +59,13 @@ def make_workload(args, rank):
         name = (f"config4: {args.field}x{args.field} synthetic crowded field -> {len(w['gn']) // 5} subdivisions of 256x256 "
                 f"(reference tiler utils.py:332-375, overlap 0) x 5 beta inits = {len(w['gn'])} beta-SGP solves, "
                 "proj_type=1, 2-D bkg, shared PSF")
+        return w, kw, name, True
+    if args.workload == "frame":
+        f = synth.single_frame(args.frame, seed=77 + rank)
+        w = dict(gn=f["gn"][None], bkg=f["bkg"][None], psf=f["psf"], flux=np.array([f["flux"]]), beta0=np.array([1.0248357076505616]))
+        kw = dict(synth.TILE_KWARGS, stop_criterion=1, MAXIT=args.maxit)
+        name = (f"config5: one synthetic {args.frame}x{args.frame} crowded frame, beta-SGP, proj_type=1, 2-D bkg, frame-sized PSF, "
+                f"{args.maxit} iterations (stop_criterion=1), frame mode (one image over the whole GPU)")
         return w, kw, name, True
     w = synth.star_stamps(args.stamps, 32, seed=12345 + rank)
     kw = dict(synth.STAMP_KWARGS)
@@ -135,12 +144,40 @@ def cpu_jobs(w, kw, shared_psf, idx):
     return jobs
 
 
+def frame_cpu_baseline(w, kw, side):
+    """The oracle needs ~40 s per iteration at 8192^2; time a 2048^2 crop for 3 iterations and scale by the pixel
+    ratio (the loop is O(N log N): the scaled figure flatters the CPU slightly)."""
+    from oracle import sgp_oracle as orc
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bsgp_synth2", os.path.join(ROOT, "beta-sgp_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    c = min(2048, side)
+    gn = np.ascontiguousarray(w["gn"][0][:c, :c]); bkg = np.ascontiguousarray(w["bkg"][0][:c, :c])
+    psf = synth.moffat_psf(c, c, 3.5)
+    k = dict(kw, MAXIT=3)
+    t0 = time.perf_counter()
+    orc.solve(gn, psf, bkg, divergence="beta", flux=np.float64((gn - bkg).sum()), betaParam=float(w["beta0"][0]), **k)
+    per_iter = (time.perf_counter() - t0) / 3.0 * (side * side) / float(c * c)
+    return {"value": 1.0 / (per_iter * kw["MAXIT"]), "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": f"{c}x{c} crop, 3 iterations of the oracle port on 1 thread, scaled by the pixel ratio to {side}x{side} and {kw['MAXIT']} iterations"}
+
+
 def run_reference(args, rank):
     """CPU arm: oracle port on all host cores, bounded sample per step."""
     if rank != 0:
         return
     import multiprocessing as mp
     w, kw, name, shared = make_workload(args, 0)
+    if args.workload == "frame":
+        cb = frame_cpu_baseline(w, kw, w["gn"].shape[-1])
+        print(json.dumps({"impl": "reference", "metric": "beta-SGP restored images/s", "value": cb["value"], "unit": "images/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": name}, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     procs = max(1, min(cores, 64))
     n = len(w["gn"])
@@ -314,16 +351,19 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, ROOT)
-            n = min(args.cpu_sample, B) if args.workload == "tiles256" else min(args.cpu_sample * 64, B)
-            idx = np.linspace(0, B - 1, n).astype(int)
-            jobs = cpu_jobs(w, kw, shared_psf, idx)
-            _oracle_solve(jobs[0])
-            t0 = time.perf_counter()
-            for j in jobs:
-                _oracle_solve(j)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": 1, "kind": "port",
-                                    "sample": f"{n} of the {B} solves (evenly spaced indices), oracle port, 1 thread, after one warm-up solve"}
+            if args.workload == "frame":
+                line["cpu_baseline"] = frame_cpu_baseline(w, kw, ny)
+            else:
+                n = min(args.cpu_sample, B) if args.workload == "tiles256" else min(args.cpu_sample * 64, B)
+                idx = np.linspace(0, B - 1, n).astype(int)
+                jobs = cpu_jobs(w, kw, shared_psf, idx)
+                _oracle_solve(jobs[0])
+                t0 = time.perf_counter()
+                for j in jobs:
+                    _oracle_solve(j)
+                dt = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": 1, "kind": "port",
+                                        "sample": f"{n} of the {B} solves (evenly spaced indices), oracle port, 1 thread, after one warm-up solve"}
         print(json.dumps(line), flush=True)
     plan.close()
     if world > 1:
