@@ -360,17 +360,24 @@ template <typename T, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const Im
 // iteration phases (sgp.py:302-425 / 748-882)
 // -------------------------------------------------------------------------------------------------
 // proj_type 1: (pending x update,) X = clip(x), c = (x - alpha X g) / X           sgp.py:311-316
-template <typename T, class Ctx> BSGP_NOINLINE void ph_trial_point(Ctx ctx, const ImgState<T>* S, T al, T lam_pending, int flags) {
+// Also returns the slab sums of x(lambda) for lambda = 0, +1, -1: the root-find always starts with lambda = 0 and
+// then tries +1 or -1 (flux_conserve_proj.py:7,22,33,58), so its first two evaluations need no pass of their own.
+template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ctx, const ImgState<T>* S, T al, T lam_pending, int flags) {
     ctx.sync();
     T* x = S->x; const T* gr = S->g; T* cbuf = S->d; T* Xbuf = S->t1;
-    const T xlo = S->xlo, xhi = S->xhi;
+    const T xlo = S->xlo, xhi = S->xhi, cap = S->cap;
+    const bool has_cap = S->has_cap != 0;
     const bool pending = (flags & F_PENDING) != 0, ones = (flags & F_XONES) != 0;
+    double s0 = 0.0, sp = 0.0, sm = 0.0;
     auto fetch = [&](int i) { In3<T> r; r.a = ld2(x, i); r.b = ld2(gr, i); r.c = pending ? ld2(cbuf, i) : mk2((T)0, (T)0); return r; };
     auto one = [&](T xv, T gv, T dv, T& xo, T& co, T& Xo) {
         if (pending) xv = nadd(xv, nmul(lam_pending, dv));
         const T X = ones ? (T)1 : clip_bounds(xv, xlo, xhi);
         const T y = nsub(xv, nmul(al, nmul(X, gv)));
         xo = xv; co = nmul(y, ndiv((T)1, X)); Xo = X;
+        s0 += (double)proj_point(co, X, (T)0, has_cap, cap);
+        sp += (double)proj_point(co, X, (T)1, has_cap, cap);
+        sm += (double)proj_point(co, X, (T)-1, has_cap, cap);
     };
     auto body = [&](int i, const In3<T>& in) {
         V2<T> xo, co, Xo;
@@ -381,6 +388,8 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_trial_point(Ctx ctx, cons
         st2(Xbuf, i, Xo);
     };
     pair_loop<4>(ctx, S->nslab, fetch, body);
+    R3 r; r.a = s0; r.b = sp; r.c = sm;
+    return r;
 }
 
 // producer of A(d): d = y - x with y the projected trial point; returns the slab part of gd = d.g   sgp.py:311-321
@@ -613,7 +622,14 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
     int total_evals = 0, total_trials = 0;
     if (pflag && !(flux > 0.0 && is_finite(flux))) status = BSGP_ST_BAD_FLUX;
 
+    bool have_pre = false;            // sums of x(lambda) at lambda = 0, +1, -1 delivered by ph_trial_point
+    double pre[3] = {0.0, 0.0, 0.0};
     auto proj_eval = [&](double lam) -> double {
+        if (have_pre) {
+            if (lam == 0.0) return pre[0] - flux;
+            if (lam == 1.0) return pre[1] - flux;
+            if (lam == -1.0) return pre[2] - flux;
+        }
         double s = ph_proj_eval<T>(ctx, S, (T)lam);
         ctx.allreduce_sum(&s, 1);
         return s - flux;
@@ -707,7 +723,12 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         int evals = 0;
         T lam_proj = (T)0;
         if (pflag) {
-            ph_trial_point<T>(ctx, S, al, lam_pending, flags);
+            {
+                const R3 t = ph_trial_point<T>(ctx, S, al, lam_pending, flags);
+                pre[0] = t.a; pre[1] = t.b; pre[2] = t.c;
+                ctx.allreduce_sum(pre, 3);
+                have_pre = true;
+            }
             pending = false;
             flags &= ~F_PENDING;
             const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
