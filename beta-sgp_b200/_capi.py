@@ -32,7 +32,8 @@ class Params(C.Structure):
         ("m", C.c_int), ("max_projs", C.c_int), ("verbose", C.c_int), ("has_flux", C.c_int), ("has_sat", C.c_int),
         ("ccd_sat_level", C.c_double), ("scale_data", C.c_int), ("errflag", C.c_int),
         ("tol_convergence", C.c_double), ("adapt_beta", C.c_int), ("lr", C.c_double), ("lr_exp_param", C.c_double),
-        ("schedule_lr", C.c_int),
+        ("schedule_lr", C.c_int), ("region", C.c_int * 4), ("div_a", C.c_double), ("div_at", C.c_double),
+        ("adjoint_second_psf", C.c_int),
     ]
 
 
@@ -58,7 +59,7 @@ class PlanInfo(C.Structure):
 def make_params(divergence, *, init_recon=0, proj_type=0, stop_criterion=0, MAXIT=500, gamma=1e-4, beta=0.4, alpha=1.3,
                 alpha_min=1e-5, alpha_max=1e5, M_alpha=3, tau=0.5, M=1, max_projs=1000, verbose=True, has_flux=False,
                 ccd_sat_level=None, scale_data=True, errflag=False, tol_convergence=1e-4, adapt_beta=True, lr=1e-3,
-                lr_exp_param=0.1, schedule_lr=False):
+                lr_exp_param=0.1, schedule_lr=False, region=None, div_a=1.0, div_at=1.0, adjoint_second_psf=False):
     p = Params()
     p.divergence = divergence
     p.init_recon, p.proj_type, p.stop_criterion, p.maxit = int(init_recon), int(proj_type), int(stop_criterion), int(MAXIT)
@@ -69,6 +70,9 @@ def make_params(divergence, *, init_recon=0, proj_type=0, stop_criterion=0, MAXI
     p.ccd_sat_level = float(ccd_sat_level) if ccd_sat_level is not None else 0.0
     p.scale_data, p.errflag, p.tol_convergence = int(bool(scale_data)), int(bool(errflag)), float(tol_convergence)
     p.adapt_beta, p.lr, p.lr_exp_param, p.schedule_lr = int(bool(adapt_beta)), float(lr), float(lr_exp_param), int(bool(schedule_lr))
+    if region is not None:
+        p.region[0], p.region[1], p.region[2], p.region[3] = (int(v) for v in region)
+    p.div_a, p.div_at, p.adjoint_second_psf = float(div_a), float(div_at), int(bool(adjoint_second_psf))
     return p
 
 
@@ -95,6 +99,8 @@ def lib():
     L.bsgp_plan_configure.argtypes = [vp, ip, ip]
     L.bsgp_set_psf.argtypes = [vp, vp, ip, vp]
     L.bsgp_set_psf_host.argtypes = [vp, vp, ip]
+    L.bsgp_set_psf_adjoint.argtypes = [vp, vp, ip, vp]
+    L.bsgp_set_psf_adjoint_host.argtypes = [vp, vp, ip]
     L.bsgp_solve_batch.argtypes = [vp, C.POINTER(Params), ip, C.POINTER(Inputs), C.POINTER(Outputs), vp]
     L.bsgp_solve_batch_host.argtypes = [vp, C.POINTER(Params), ip, C.POINTER(Inputs), C.POINTER(Outputs)]
     L.bsgp_apply_psf.argtypes = [vp, vp, vp, ip, ip, vp]
@@ -117,6 +123,6 @@ def check(rc):
 
 
 EXPORTED = ["bsgp_plan_create", "bsgp_plan_destroy", "bsgp_plan_get_info", "bsgp_plan_configure", "bsgp_set_psf",
-            "bsgp_set_psf_host", "bsgp_solve_batch", "bsgp_solve_batch_host", "bsgp_apply_psf", "bsgp_apply_psf_host",
+            "bsgp_set_psf_host", "bsgp_set_psf_adjoint", "bsgp_set_psf_adjoint_host", "bsgp_solve_batch", "bsgp_solve_batch_host", "bsgp_apply_psf", "bsgp_apply_psf_host",
             "bsgp_project_df", "bsgp_project_df_host", "bsgp_beta_div_host", "bsgp_beta_grad_terms_host", "bsgp_device_count",
             "bsgp_last_error_string", "bsgp_version"]

@@ -229,6 +229,7 @@ struct bsgp_plan {
     int threads = 0, minb = 1, num_clusters = 0, conv_clusters = 0, resident_mask = 0;
     void* twx = nullptr; void* twy = nullptr;
     void* tf = nullptr; int n_psf = 0; int tf_capacity = 0; size_t tf_stride = 0;
+    void* tf_adj = nullptr; int n_psf_adj = 0; int tf_adj_capacity = 0;   // spectra of the second (adjoint) kernel
     void* work = nullptr; size_t work_stride = 0;
     void* spec = nullptr; size_t spec_stride = 0;
     int* queue = nullptr;
@@ -240,9 +241,9 @@ struct bsgp_plan {
 template <typename T> static const void* conv_kernel_ptr() { return (const void*)bsgp_conv_kernel<T>; }
 
 static void plan_free_buffers(bsgp_plan* p) {
-    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue); cudaFree(p->gpart);
+    cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->tf_adj); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue); cudaFree(p->gpart);
     p->twx = p->twy = p->tf = p->work = p->spec = nullptr; p->queue = nullptr; p->gpart = nullptr;
-    p->tf_capacity = 0; p->n_psf = 0;
+    p->tf_capacity = 0; p->n_psf = 0; p->tf_adj = nullptr; p->tf_adj_capacity = 0; p->n_psf_adj = 0;
 }
 
 static inline size_t up128(size_t v) { return (v + 127) & ~(size_t)127; }
@@ -299,7 +300,7 @@ template <typename T> static int plan_setup_frame(bsgp_plan* p) {
     if (!coop) return fail(BSGP_E_CUDA, "device does not support cooperative launches (frame mode)");
     LaunchCfg lc{G, 512, 1, p->smem_bytes, nullptr, 1};
     int per_sm = 0;
-    cudaError_t e = query_frame_ctas<T>(lc, &per_sm);
+    cudaError_t e = query_frame_ctas<T, false>(lc, &per_sm);
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     if (per_sm < 1) return fail(BSGP_E_CUDA, "frame kernel does not fit: %zu B shared memory", p->smem_bytes);
     CU(cudaFuncSetAttribute(conv_frame_kernel_ptr<T>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->conv_smem));
@@ -392,7 +393,7 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
         return fail(BSGP_E_SHAPE, "shape %dx%d needs %zu B of shared memory per CTA (limit %d)", p->ny, p->nx, p->smem_bytes, p->max_smem);
     LaunchCfg lc{G * p->num_sms, threads, G, p->smem_bytes, nullptr, p->minb};
     int nc = 0;
-    cudaError_t e = query_solve_clusters<T>(lc, p->num_sms, &nc);
+    cudaError_t e = query_solve_clusters<T, false>(lc, p->num_sms, &nc);
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     if (nc <= 0) return fail(BSGP_E_CUDA, "kernel does not fit: cluster %d, %d threads, %zu B shared memory", G, threads, p->smem_bytes);
     p->num_clusters = nc;
@@ -445,17 +446,19 @@ template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int c
     return BSGP_OK;
 }
 
-template <typename T> static int set_psf_t(bsgp_plan* p, const void* psf_dev, int n_psf, cudaStream_t st) {
-    if (n_psf > p->tf_capacity) {
-        cudaFree(p->tf); p->tf = nullptr; p->tf_capacity = 0;
-        CU(cudaMalloc(&p->tf, (size_t)n_psf * p->tf_stride * sizeof(cplx<T>)));
-        p->tf_capacity = n_psf;
+template <typename T> static int set_psf_t(bsgp_plan* p, const void* psf_dev, int n_psf, cudaStream_t st, bool adjoint_kernel = false) {
+    void*& tfbuf = adjoint_kernel ? p->tf_adj : p->tf;
+    int& cap = adjoint_kernel ? p->tf_adj_capacity : p->tf_capacity;
+    if (n_psf > cap) {
+        cudaFree(tfbuf); tfbuf = nullptr; cap = 0;
+        CU(cudaMalloc(&tfbuf, (size_t)n_psf * p->tf_stride * sizeof(cplx<T>)));
+        cap = n_psf;
     }
-    p->n_psf = n_psf;
+    (adjoint_kernel ? p->n_psf_adj : p->n_psf) = n_psf;
     ConvArgs<T> a;
     memset(&a, 0, sizeof a);
     a.g = p->g; a.count = n_psf; a.in = (const T*)psf_dev; a.out = nullptr;
-    a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = n_psf; a.tf_stride = p->tf_stride;
+    a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)tfbuf; a.n_psf = n_psf; a.tf_stride = p->tf_stride;
     a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride; a.mode = CONV_MAKE_TF; a.queue = p->queue;
     return launch_conv<T>(p, a, n_psf, st);
 }
@@ -477,6 +480,7 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     a.gn = (const T*)in->gn; a.bkg = (const T*)in->bkg; a.bkg_is_image = in->bkg_is_image; a.flux = in->flux; a.beta0 = in->beta0;
     a.x0 = (const T*)in->x0; a.obj = (const T*)in->obj; a.order = in->order;
     a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = p->n_psf;
+    a.tf_adj = prm->adjoint_second_psf ? (cplx<T>*)p->tf_adj : nullptr;
     a.work = (T*)p->work; a.work_stride = p->work_stride; a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride;
     a.resident_mask = p->resident_mask;
     a.x_out = (T*)out->x; a.iters = out->iters; a.status = out->status; a.discr = out->discr; a.times = out->times;
@@ -486,14 +490,16 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     a.queue = p->queue;
     if (p->frame) {
         LaunchCfg fc{p->g.G, 512, 1, p->smem_bytes, st, 1};
-        cudaError_t fe = launch_frame<T>(fc, a, p->sp, p->tf_stride, p->gpart);
+        const bool mk = prm->region[1] > prm->region[0];
+        cudaError_t fe = mk ? launch_frame<T, true>(fc, a, p->sp, p->tf_stride, p->gpart) : launch_frame<T, false>(fc, a, p->sp, p->tf_stride, p->gpart);
         if (fe != cudaSuccess) return fail(BSGP_E_CUDA, "frame kernel launch failed: %s", cudaGetErrorString(fe));
         return BSGP_OK;
     }
     CU(cudaMemsetAsync(p->queue, 0, sizeof(int), st));
     const int nclu = batch < p->num_clusters ? batch : p->num_clusters;
     LaunchCfg lc{nclu * p->g.G, p->threads, p->g.G, p->smem_bytes, st, p->minb};
-    cudaError_t e = launch_solve<T>(lc, a, p->sp, p->tf_stride);
+    const bool mk = prm->region[1] > prm->region[0];
+    cudaError_t e = mk ? launch_solve<T, true>(lc, a, p->sp, p->tf_stride) : launch_solve<T, false>(lc, a, p->sp, p->tf_stride);
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "solve kernel launch failed: %s", cudaGetErrorString(e));
     return BSGP_OK;
 }
@@ -593,6 +599,27 @@ int bsgp_set_psf_host(bsgp_plan* p, const void* psf_host, int n_psf) {
     return rc;
 }
 
+int bsgp_set_psf_adjoint(bsgp_plan* p, const void* psf_dev, int n_psf, void* stream) {
+    if (!p || !psf_dev || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (misaligned(psf_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
+    CU(cudaSetDevice(p->device));
+    return p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, (cudaStream_t)stream, true)
+                                : set_psf_t<float>(p, psf_dev, n_psf, (cudaStream_t)stream, true);
+}
+
+int bsgp_set_psf_adjoint_host(bsgp_plan* p, const void* psf_host, int n_psf) {
+    if (!p || !psf_host || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
+    CU(cudaSetDevice(p->device));
+    const size_t bytes = (size_t)n_psf * p->ny * p->nx * p->elem;
+    void* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpy(d, psf_host, bytes, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? bsgp_set_psf_adjoint(p, d, n_psf, nullptr) : fail(BSGP_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    if (rc == BSGP_OK) { e = cudaDeviceSynchronize(); if (e != cudaSuccess) rc = fail(BSGP_E_CUDA, "PSF spectrum kernel failed: %s", cudaGetErrorString(e)); }
+    cudaFree(d);
+    return rc;
+}
+
 int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream) {
     if (!p || !prm || !in || !out) return fail(BSGP_E_ARG, "NULL argument");
     if (batch < 1) return fail(BSGP_E_ARG, "batch must be >= 1");
@@ -604,6 +631,14 @@ int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp
     if (prm->divergence == BSGP_DIV_BETA && !in->beta0) return fail(BSGP_E_ARG, "beta-divergence needs inputs.beta0");
     if (prm->init_recon == 1 && !in->x0) return fail(BSGP_E_ARG, "init_recon = 1 needs inputs.x0");
     if (prm->errflag && (!in->obj || !out->err)) return fail(BSGP_E_ARG, "errflag needs inputs.obj and outputs.err");
+    if (prm->adjoint_second_psf && (p->tf_adj == nullptr || p->n_psf_adj != p->n_psf))
+        return fail(BSGP_E_STATE, "adjoint_second_psf set but bsgp_set_psf_adjoint was not called with the same number of PSFs");
+    if (prm->region[1] > prm->region[0] || prm->region[3] > prm->region[2]) {
+        const int* r = prm->region;
+        if (r[0] < 0 || r[1] > p->ny || r[2] < 0 || r[3] > p->nx || r[1] <= r[0] || r[3] <= r[2])
+            return fail(BSGP_E_ARG, "region {%d, %d, %d, %d} does not fit the %dx%d grid", r[0], r[1], r[2], r[3], p->ny, p->nx);
+        if (!(prm->div_a > 0.0) || !(prm->div_at > 0.0)) return fail(BSGP_E_ARG, "div_a / div_at must be positive when a region is set");
+    }
     if (misaligned(in->gn) || misaligned(out->x) || misaligned(in->x0) || misaligned(in->obj) || (in->bkg_is_image && misaligned(in->bkg)))
         return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));

@@ -61,10 +61,10 @@ static inline cudaError_t query_clusters(const void* func, const LaunchCfg& lc, 
     return e;
 }
 
-// defined in bsgp_solve_f64.cu / bsgp_solve_f32.cu
-template <typename T> cudaError_t launch_solve(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride);
-template <typename T> cudaError_t query_solve_clusters(const LaunchCfg& lc, int num_sms, int* out);
-template <typename T> cudaError_t launch_frame(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride, double* gpart);
-template <typename T> cudaError_t query_frame_ctas(const LaunchCfg& lc, int* per_sm);
+// defined in bsgp_solve_f64.cu / bsgp_solve_f32.cu (MK = false) and bsgp_solve_f64_padded.cu / bsgp_solve_f32_padded.cu (MK = true)
+template <typename T, bool MK> cudaError_t launch_solve(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride);
+template <typename T, bool MK> cudaError_t query_solve_clusters(const LaunchCfg& lc, int num_sms, int* out);
+template <typename T, bool MK> cudaError_t launch_frame(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride, double* gpart);
+template <typename T, bool MK> cudaError_t query_frame_ctas(const LaunchCfg& lc, int* per_sm);
 
 }  // namespace bsgp

@@ -1,5 +1,6 @@
 // The persistent solve kernel and its launchers.  Included by one translation unit per data type
-// (bsgp_solve_f64.cu, bsgp_solve_f32.cu) so the two compile in parallel.
+// and operator kind (bsgp_solve_f64.cu, bsgp_solve_f32.cu, *_padded.cu) so they compile in parallel.  MK = true is the
+// zero-padded operator (valid-window masks compiled in); MK = false the circular one (no mask code at all).
 #pragma once
 #include <string.h>
 
@@ -9,7 +10,7 @@
 
 namespace bsgp {
 
-template <typename T, int NT, int MINB>
+template <typename T, int NT, int MINB, bool MK>
 __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
     unsigned char* smem = dyn_smem();
     DeviceCtx ctx = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
@@ -47,12 +48,13 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
         if (item >= a.batch) break;
         const int img = a.order ? a.order[item] : item;
         cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
-        solve_image<T>(ctx, a, S, buf, tf, img);
+        cplx<T>* tfa = a.tf_adj ? a.tf_adj + (a.n_psf > 1 ? (size_t)img * tf_stride : 0) : tf;
+        solve_image<T, MK>(ctx, a, S, buf, tf, tfa, img);
     }
 }
 
 // Frame mode (GridCtx): the images of the batch are restored one after the other, each by the whole grid.
-template <typename T>
+template <typename T, bool MK>
 __global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride, double* gpart) {
     unsigned char* smem = dyn_smem();
     GridCtx ctx = make_grid_ctx(reinterpret_cast<SharedCtl*>(smem), gpart);
@@ -81,49 +83,50 @@ __global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a
     __syncthreads();
     for (int img = 0; img < a.batch; ++img) {
         cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
-        solve_image<T>(ctx, a, S, buf, tf, img);
+        cplx<T>* tfa = a.tf_adj ? a.tf_adj + (a.n_psf > 1 ? (size_t)img * tf_stride : 0) : tf;
+        solve_image<T, MK>(ctx, a, S, buf, tf, tfa, img);
         ctx.cluster_sync();          // the scratch arrays and the exchange buffer are reused by the next image
     }
 }
 
-template <typename T>
+template <typename T, bool MK>
 cudaError_t launch_frame(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride, double* gpart) {
     SolveArgs<T> args = a;
     SmemPlan plan = sp;
     size_t tfs = tf_stride;
     double* gp = gpart;
     void* params[] = {&args, &plan, &tfs, &gp};
-    const void* fn = (const void*)bsgp_frame_kernel<T>;
+    const void* fn = (const void*)bsgp_frame_kernel<T, MK>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
     if (e != cudaSuccess) return e;
     return cudaLaunchCooperativeKernel(fn, dim3(lc.grid), dim3(lc.threads), params, lc.smem, lc.stream);
 }
 
-template <typename T> cudaError_t query_frame_ctas(const LaunchCfg& lc, int* per_sm) {
-    const void* fn = (const void*)bsgp_frame_kernel<T>;
+template <typename T, bool MK> cudaError_t query_frame_ctas(const LaunchCfg& lc, int* per_sm) {
+    const void* fn = (const void*)bsgp_frame_kernel<T, MK>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, lc.threads, lc.smem);
 }
 
 // register budgets: 512 x 128, 256 x 255 (one CTA per SM), 256 x 128 (two CTAs per SM), 128 x 168 (three), 128 x 128 (four)
-template <typename T> static const void* solve_kernel_ptr(int threads, int minb) {
-    if (threads <= 128) return minb >= 4 ? (const void*)bsgp_solve_kernel<T, 128, 4> : (const void*)bsgp_solve_kernel<T, 128, 3>;
-    if (threads <= 256) return minb >= 2 ? (const void*)bsgp_solve_kernel<T, 256, 2> : (const void*)bsgp_solve_kernel<T, 256, 1>;
-    return (const void*)bsgp_solve_kernel<T, 512, 1>;
+template <typename T, bool MK> static const void* solve_kernel_ptr(int threads, int minb) {
+    if (threads <= 128) return minb >= 4 ? (const void*)bsgp_solve_kernel<T, 128, 4, MK> : (const void*)bsgp_solve_kernel<T, 128, 3, MK>;
+    if (threads <= 256) return minb >= 2 ? (const void*)bsgp_solve_kernel<T, 256, 2, MK> : (const void*)bsgp_solve_kernel<T, 256, 1, MK>;
+    return (const void*)bsgp_solve_kernel<T, 512, 1, MK>;
 }
 
-template <typename T>
+template <typename T, bool MK>
 cudaError_t launch_solve(const LaunchCfg& lc, const SolveArgs<T>& a, const SmemPlan& sp, size_t tf_stride) {
     SolveArgs<T> args = a;
     SmemPlan plan = sp;
     size_t tfs = tf_stride;
     void* params[] = {&args, &plan, &tfs};
-    return launch_clustered(solve_kernel_ptr<T>(lc.threads, lc.minb), lc, params);
+    return launch_clustered(solve_kernel_ptr<T, MK>(lc.threads, lc.minb), lc, params);
 }
 
-template <typename T> cudaError_t query_solve_clusters(const LaunchCfg& lc, int num_sms, int* out) {
-    return query_clusters(solve_kernel_ptr<T>(lc.threads, lc.minb), lc, num_sms, out);
+template <typename T, bool MK> cudaError_t query_solve_clusters(const LaunchCfg& lc, int num_sms, int* out) {
+    return query_clusters(solve_kernel_ptr<T, MK>(lc.threads, lc.minb), lc, num_sms, out);
 }
 
 }  // namespace bsgp

@@ -41,7 +41,7 @@ template <typename T> struct SolveArgs {
     // inputs
     const T* gn; const T* bkg; int bkg_is_image; const double* flux; const double* beta0; const T* x0; const T* obj; const int* order;
     // tables
-    const cplx<T>* twx; const cplx<T>* twy; cplx<T>* tf; int n_psf;
+    const cplx<T>* twx; const cplx<T>* twy; cplx<T>* tf; cplx<T>* tf_adj; int n_psf;
     // per-cluster global scratch
     T* work; size_t work_stride; cplx<T>* spec; size_t spec_stride;
     int resident_mask;              // bit b: Buf b lives in shared memory
@@ -61,7 +61,9 @@ template <typename T> struct ImgState {
     unsigned twx_off, twy_off;       // twiddle tables in shared memory, or kNoSmem (then twx / twy are used)
     ConvGeom geom;
     int nslab, bkg_img, init_recon, has_cap, pflag, want_err, stop2;
+    int masked, reg[4];              // zero-padded operator: valid window [reg0, reg1) x [reg2, reg3) of the FFT grid
     T bkg_raw_s, scaling, bkg_s, null_fill, x_const, cap, xlo, xhi;
+    T div_a, div_at;                 // output divisors of A / A^T (zero-padded operator; 1 otherwise)
 };
 
 struct R2 { double a, b; };
@@ -156,55 +158,80 @@ template <typename T> BSGP_DEV T proj_point(T c, T X, T lam, bool has_cap, T cap
 }
 
 // -------------------------------------------------------------------------------------------------
+// Valid region.  With the zero-padded operator (the reference's astropy closure, sgp.py:121-161) the
+// image occupies a centred window [r0, r1) x [c0, c1) of the power-of-two FFT grid the kernel works on;
+// everything outside is padding: it holds zeros in every array, contributes to no sum, and operator
+// outputs that land there are discarded.  With the circular operator the region is the whole grid and
+// `on` is 0 (every test below folds to true).
+// -------------------------------------------------------------------------------------------------
+struct Region { int on, r0, r1, c0, c1, row_off, lg_nx, colmask; };
+template <bool MK, typename T, class Ctx> BSGP_DEV Region region_of(const Ctx& ctx, const ImgState<T>* S) {
+    Region R;
+    R.on = MK;
+    if (!MK) { R.r0 = R.r1 = R.c0 = R.c1 = R.row_off = R.lg_nx = R.colmask = 0; return R; } R.r0 = S->reg[0]; R.r1 = S->reg[1]; R.c0 = S->reg[2]; R.c1 = S->reg[3];
+    R.row_off = ctx.rank * S->geom.rows_per_cta; R.lg_nx = S->geom.lg_nx; R.colmask = S->geom.nx - 1;
+    return R;
+}
+template <bool MK> BSGP_DEV bool inside(const Region& R, int i) {
+    if (!MK) return true;
+    const int row = R.row_off + (i >> R.lg_nx), col = i & R.colmask;
+    return row >= R.r0 && row < R.r1 && col >= R.c0 && col < R.c1;
+}
+
+// -------------------------------------------------------------------------------------------------
 // setup phases (sgp.py:166-217, 248-257)
 // -------------------------------------------------------------------------------------------------
 // sum(gn), sum(gn - bkg), max(gn) over the raw slab
-template <typename T, class Ctx> BSGP_NOINLINE R3 ph_stats(Ctx ctx, const ImgState<T>* S) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_stats(Ctx ctx, const ImgState<T>* S) {
     ctx.sync();
     const T* gr = S->gn_raw; const T* br = S->bkg_raw; const bool bimg = S->bkg_img != 0; const T bs = S->bkg_raw_s;
+    const Region R = region_of<MK>(ctx, S);
     double mx = -INFINITY, s0 = 0.0, s1 = 0.0;
     auto fetch = [&](int i) { In2<T> r; r.a = ld2(gr, i); r.b = bimg ? ld2(br, i) : mk2(bs, bs); return r; };
-    auto body = [&](int, const In2<T>& in) {
-        mx = ((double)in.a.x > mx) ? (double)in.a.x : mx;
-        s0 += (double)in.a.x;
-        s1 += (double)nsub(in.a.x, in.b.x);
-        mx = ((double)in.a.y > mx) ? (double)in.a.y : mx;
-        s0 += (double)in.a.y;
-        s1 += (double)nsub(in.a.y, in.b.y);
+    auto one = [&](bool m, T v, T b) {
+        if (!m) return;
+        mx = ((double)v > mx) ? (double)v : mx;
+        s0 += (double)v;
+        s1 += (double)nsub(v, b);
     };
+    auto body = [&](int i, const In2<T>& in) { one(inside<MK>(R, i), in.a.x, in.b.x); one(inside<MK>(R, i + 1), in.a.y, in.b.y); };
     pair_loop<4>(ctx, S->nslab, fetch, body);
     R3 r; r.a = s0; r.b = s1; r.c = mx;
     return r;
 }
 
 // gn = gn_raw / scaling; returns the smallest positive scaled value
-template <typename T, class Ctx> BSGP_NOINLINE double ph_scale_gn(Ctx ctx, const ImgState<T>* S) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_scale_gn(Ctx ctx, const ImgState<T>* S) {
     ctx.sync();
     const T* gr = S->gn_raw; T* gn = S->gn; const T scaling = S->scaling;
+    const Region R = region_of<MK>(ctx, S);
     double vmin = INFINITY;
     auto fetch = [&](int i) { In1<T> r; r.a = ld2(gr, i); return r; };
     auto body = [&](int i, const In1<T>& in) {
-        const V2<T> v = mk2(ndiv(in.a.x, scaling), ndiv(in.a.y, scaling));
+        const bool m0 = inside<MK>(R, i), m1 = inside<MK>(R, i + 1);
+        const V2<T> v = mk2(m0 ? ndiv(in.a.x, scaling) : (T)0, m1 ? ndiv(in.a.y, scaling) : (T)0);
         st2(gn, i, v);
-        if (v.x > (T)0 && (double)v.x < vmin) vmin = (double)v.x;
-        if (v.y > (T)0 && (double)v.y < vmin) vmin = (double)v.y;
+        if (m0 && v.x > (T)0 && (double)v.x < vmin) vmin = (double)v.x;
+        if (m1 && v.y > (T)0 && (double)v.y < vmin) vmin = (double)v.y;
     };
     pair_loop<4>(ctx, S->nslab, fetch, body);
     return vmin;
 }
 
 // null-pixel fix, scaled background, start image; returns sum(gn - bkg)
-template <typename T, class Ctx> BSGP_NOINLINE double ph_init(Ctx ctx, const ImgState<T>* S) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_init(Ctx ctx, const ImgState<T>* S) {
     ctx.sync();
     T* gn = S->gn; T* bkgb = S->bkg; T* x = S->x; const T* br = S->bkg_raw; const T* x0 = S->x0_raw;
     const bool bimg = S->bkg_img != 0; const int init = S->init_recon;
     const T scaling = S->scaling, null_fill = S->null_fill, bkg_s = S->bkg_s, x_const = S->x_const;
+    const Region R = region_of<MK>(ctx, S);
     double sum = 0.0;
     auto fetch = [&](int i) {
         In3<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(br, i) : mk2(bkg_s, bkg_s); r.c = (init == 1) ? ld2(x0, i) : mk2((T)0, (T)0);
         return r;
     };
-    auto one = [&](T v0, T braw, T x0v, T& gfix, T& bk, T& xv) {
+    auto one = [&](bool m, T v0, T braw, T x0v, T& gfix, T& bk, T& xv) {
+        if (!m) { gfix = (T)0; bk = (T)0; xv = (T)0; return; }
         gfix = (v0 <= (T)0) ? null_fill : v0;
         bk = bimg ? ndiv(braw, scaling) : bkg_s;
         sum += (double)nsub(gfix, bk);
@@ -215,9 +242,9 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_init(Ctx ctx, const Img
     };
     auto body = [&](int i, const In3<T>& in) {
         V2<T> gf, bk, xv;
-        one(in.a.x, in.b.x, in.c.x, gf.x, bk.x, xv.x);
-        one(in.a.y, in.b.y, in.c.y, gf.y, bk.y, xv.y);
-        if (in.a.x <= (T)0 || in.a.y <= (T)0) st2(gn, i, gf);
+        one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, gf.x, bk.x, xv.x);
+        one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, gf.y, bk.y, xv.y);
+        if (gf.x != in.a.x || gf.y != in.a.y) st2(gn, i, gf);
         if (bimg) st2(bkgb, i, bk);
         st2(x, i, xv);
     };
@@ -238,51 +265,57 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_proj_init_load(Ctx ctx, c
 }
 
 // r(lambda) + b = sum_i x_i(lambda) over the slab                       flux_conserve_proj.py:22-25
-template <typename T, class Ctx> BSGP_NOINLINE double ph_proj_eval(Ctx ctx, const ImgState<T>* S, T lam) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_proj_eval(Ctx ctx, const ImgState<T>* S, T lam) {
     ctx.sync();
     const T* cbuf = S->d; const T* Xbuf = S->t1; const bool has_cap = S->has_cap != 0; const T cap = S->cap;
+    const Region R = region_of<MK>(ctx, S);
     double s = 0.0;
     auto fetch = [&](int i) { In2<T> r; r.a = ld2(cbuf, i); r.b = ld2(Xbuf, i); return r; };
-    auto body = [&](int, const In2<T>& in) {
-        s += (double)proj_point(in.a.x, in.b.x, lam, has_cap, cap);
-        s += (double)proj_point(in.a.y, in.b.y, lam, has_cap, cap);
+    auto body = [&](int i, const In2<T>& in) {
+        if (inside<MK>(R, i)) s += (double)proj_point(in.a.x, in.b.x, lam, has_cap, cap);
+        if (inside<MK>(R, i + 1)) s += (double)proj_point(in.a.y, in.b.y, lam, has_cap, cap);
     };
     pair_loop<8>(ctx, S->nslab, fetch, body);
     return s;
 }
 
-template <typename T, class Ctx> BSGP_NOINLINE void ph_proj_init_store(Ctx ctx, const ImgState<T>* S, T lam) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_proj_init_store(Ctx ctx, const ImgState<T>* S, T lam) {
     ctx.sync();
     const T* cbuf = S->d; T* x = S->x; const bool has_cap = S->has_cap != 0; const T cap = S->cap;
+    const Region R = region_of<MK>(ctx, S);
     auto fetch = [&](int i) { In1<T> r; r.a = ld2(cbuf, i); return r; };
     auto body = [&](int i, const In1<T>& in) {
-        st2(x, i, mk2(proj_point(in.a.x, (T)1, lam, has_cap, cap), proj_point(in.a.y, (T)1, lam, has_cap, cap)));
+        st2(x, i, mk2(inside<MK>(R, i) ? proj_point(in.a.x, (T)1, lam, has_cap, cap) : (T)0,
+                      inside<MK>(R, i + 1) ? proj_point(in.a.y, (T)1, lam, has_cap, cap) : (T)0));
     };
     pair_loop<4>(ctx, S->nslab, fetch, body);
 }
 
 // errflag, iteration 0: |x - obj|^2, |obj|^2                            sgp.py:240-244, 255-257
-template <typename T, class Ctx> BSGP_NOINLINE R2 ph_err0(Ctx ctx, const ImgState<T>* S) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R2 ph_err0(Ctx ctx, const ImgState<T>* S) {
     ctx.sync();
     const T* truth = S->truth; const T* x = S->x; const T scaling = S->scaling;
+    const Region R = region_of<MK>(ctx, S);
     double e0 = 0.0, e1 = 0.0;
     auto fetch = [&](int i) { In2<T> r; r.a = ld2(truth, i); r.b = ld2(x, i); return r; };
-    auto one = [&](T tr, T xv) {
+    auto one = [&](bool m, T tr, T xv) {
+        if (!m) return;
         const T t = ndiv(tr, scaling);
         const T e = nsub(xv, t);
         e0 += (double)nmul(e, e);
         e1 += (double)nmul(t, t);
     };
-    auto body = [&](int, const In2<T>& in) { one(in.a.x, in.b.x); one(in.a.y, in.b.y); };
+    auto body = [&](int i, const In2<T>& in) { one(inside<MK>(R, i), in.a.x, in.b.x); one(inside<MK>(R, i + 1), in.a.y, in.b.y); };
     pair_loop<4>(ctx, S->nslab, fetch, body);
     R2 r; r.a = e0; r.b = e1;
     return r;
 }
 
 // -------------------------------------------------------------------------------------------------
-// row passes of the PSF operator with the neighbouring elementwise work fused in
+// row passes of the PSF operator with the neighbouring elementwise work fused in.  `div` is the operator's
+// output divisor: 1 for the circular operator, the kernel-weight constant of the zero-padded one.
 // -------------------------------------------------------------------------------------------------
-// producer: plain copy of x (which = 0) or gn (which = 1)
+// producer: plain copy of x (which = 0) or gn (which = 1); both are zero in the padding
 template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const ImgState<T>* S, int which) {
     ctx.sync();
     const T* src = which ? S->gn : S->x;
@@ -292,17 +325,23 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
-template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
-    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
+    const Region R = region_of<MK>(ctx, S);
     KSum acc[3];
     acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto cf = [&](int i) { In2<T> r; r.a = ld2(gn, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
+    auto one = [&](bool m, T gnv, T bk, T v, T& xt, T& p) {
+        if (!m) { xt = (T)0; p = (T)0; return; }
+        xt = MK ? ndiv(v, div) : v;
+        p = objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+    };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
-        st2(xtf, i, v);
-        V2<T> p;
-        p.x = objective_pixel(dk, in.a.x, nadd(v.x, in.b.x), v.x, want_s1 != 0, acc);
-        p.y = objective_pixel(dk, in.a.y, nadd(v.y, in.b.y), v.y, want_s1 != 0, acc);
+        V2<T> xt, p;
+        one(inside<MK>(R, i), in.a.x, in.b.x, v.x, xt.x, p.x);
+        one(inside<MK>(R, i + 1), in.a.y, in.b.y, v.y, xt.y, p.y);
+        st2(xtf, i, xt);
         st2(t1, i, p);
     };
     conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
@@ -312,10 +351,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgS
 
 // producer of the gradient's A^T argument: gn/den (KL, cached) or gn*den^(beta-2) = gn*(den^(beta-1)/den).
 // Unless F_FIRST, the accepted step is applied to x_tf on the way (x_tf += lam*d_tf, sgp.py:340).
-template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx, const ImgState<T>* S, int kind, T lam, int flags) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx, const ImgState<T>* S, int kind, T lam, int flags) {
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; const T* dtf = S->dtf; const T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const bool first = (flags & F_FIRST) != 0;
+    const Region R = region_of<MK>(ctx, S);
     auto pf = [&](int i) {
         In5<T> r; r.a = ld2(xtf, i); r.b = first ? mk2((T)0, (T)0) : ld2(dtf, i); r.c = ld2(t1, i);
         r.d = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.e = ld2(gn, i); return r;
@@ -323,34 +363,42 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx, const Im
     auto pe = [&](int i, const In5<T>& in) -> V2<T> {
         V2<T> xt = in.a;
         if (!first) { xt = mk2(nadd(in.a.x, nmul(lam, in.b.x)), nadd(in.a.y, nmul(lam, in.b.y))); st2(xtf, i, xt); }
-        if (kind == 0) return in.c;
-        return mk2(nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))), nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))));
+        if (kind == 0) return in.c;                        // the cache is zero in the padding
+        return mk2(inside<MK>(R, i) ? nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))) : (T)0,
+                   inside<MK>(R, i + 1) ? nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))) : (T)0);
     };
     conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer: g = 1 - w (KL) or den^(beta-1) - w                            sgp.py:262 / 705
-template <typename T, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx, const ImgState<T>* S, int kind) {
-    const T* t1 = S->t1; T* gr = S->g;
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx, const ImgState<T>* S, int kind) {
+    const T* t1 = S->t1; T* gr = S->g; const T div = S->div_at;
+    const Region R = region_of<MK>(ctx, S);
     auto cf = [&](int i) { In1<T> r; r.a = ld2(t1, i); return r; };
-    auto ca = [&](int i, const In1<T>& in, V2<T> w) {
-        st2(gr, i, (kind == 0) ? mk2(nsub((T)1, w.x), nsub((T)1, w.y)) : mk2(nsub(in.a.x, w.x), nsub(in.a.y, w.y)));
+    auto one = [&](bool m, T p1, T w) -> T {
+        if (!m) return (T)0;
+        if (MK) w = ndiv(w, div);
+        return (kind == 0) ? nsub((T)1, w) : nsub(p1, w);
     };
+    auto ca = [&](int i, const In1<T>& in, V2<T> w) { st2(gr, i, mk2(one(inside<MK>(R, i), in.a.x, w.x), one(inside<MK>(R, i + 1), in.a.y, w.y))); };
     conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
 }
 
 // consumer: bounds of the scaling matrix from y = flux/(flux+bkg) * A^T(gn)     sgp.py:268-270 / 712-714
-template <typename T, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const ImgState<T>* S, double flux) {
-    const T* bkgb = S->bkg; const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const ImgState<T>* S, double flux) {
+    const T* bkgb = S->bkg; const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_at;
+    const Region R = region_of<MK>(ctx, S);
     double lo = INFINITY, hi = -INFINITY;
     auto cf = [&](int i) { In1<T> r; r.a = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); return r; };
-    auto one = [&](T b, T w) {
+    auto one = [&](bool m, T b, T w) {
+        if (!m) return;
+        if (MK) w = ndiv(w, div);
         const T ratio = (T)ndiv(flux, nadd(flux, (double)b));
         const double yv = (double)nmul(ratio, w);
         if (yv > 0.0 && yv < lo) lo = yv;
         if (yv > hi) hi = yv;
     };
-    auto ca = [&](int, const In1<T>& in, V2<T> w) { one(in.a.x, w.x); one(in.a.y, w.y); };
+    auto ca = [&](int i, const In1<T>& in, V2<T> w) { one(inside<MK>(R, i), in.a.x, w.x); one(inside<MK>(R, i + 1), in.a.y, w.y); };
     conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
     R2 r; r.a = lo; r.b = hi;
     return r;
@@ -362,15 +410,17 @@ template <typename T, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx, const Im
 // proj_type 1: (pending x update,) X = clip(x), c = (x - alpha X g) / X           sgp.py:311-316
 // Also returns the slab sums of x(lambda) for lambda = 0, +1, -1: the root-find always starts with lambda = 0 and
 // then tries +1 or -1 (flux_conserve_proj.py:7,22,33,58), so its first two evaluations need no pass of their own.
-template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ctx, const ImgState<T>* S, T al, T lam_pending, int flags) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ctx, const ImgState<T>* S, T al, T lam_pending, int flags) {
     ctx.sync();
     T* x = S->x; const T* gr = S->g; T* cbuf = S->d; T* Xbuf = S->t1;
     const T xlo = S->xlo, xhi = S->xhi, cap = S->cap;
     const bool has_cap = S->has_cap != 0;
     const bool pending = (flags & F_PENDING) != 0, ones = (flags & F_XONES) != 0;
+    const Region R = region_of<MK>(ctx, S);
     double s0 = 0.0, sp = 0.0, sm = 0.0;
     auto fetch = [&](int i) { In3<T> r; r.a = ld2(x, i); r.b = ld2(gr, i); r.c = pending ? ld2(cbuf, i) : mk2((T)0, (T)0); return r; };
-    auto one = [&](T xv, T gv, T dv, T& xo, T& co, T& Xo) {
+    auto one = [&](bool m, T xv, T gv, T dv, T& xo, T& co, T& Xo) {
+        if (!m) { xo = (T)0; co = (T)0; Xo = (T)1; return; }
         if (pending) xv = nadd(xv, nmul(lam_pending, dv));
         const T X = ones ? (T)1 : clip_bounds(xv, xlo, xhi);
         const T y = nsub(xv, nmul(al, nmul(X, gv)));
@@ -381,8 +431,8 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ctx, const 
     };
     auto body = [&](int i, const In3<T>& in) {
         V2<T> xo, co, Xo;
-        one(in.a.x, in.b.x, in.c.x, xo.x, co.x, Xo.x);
-        one(in.a.y, in.b.y, in.c.y, xo.y, co.y, Xo.y);
+        one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, xo.x, co.x, Xo.x);
+        one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, xo.y, co.y, Xo.y);
         if (pending) st2(x, i, xo);
         st2(cbuf, i, co);
         st2(Xbuf, i, Xo);
@@ -393,12 +443,13 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ctx, const 
 }
 
 // producer of A(d): d = y - x with y the projected trial point; returns the slab part of gd = d.g   sgp.py:311-321
-template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const ImgState<T>* S, T al, T lam_proj, T lam_pending, int flags) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const ImgState<T>* S, T al, T lam_proj, T lam_pending, int flags) {
     ctx.sync();
     T* x = S->x; const T* gr = S->g; T* dbuf = S->d; const T* Xbuf = S->t1;
     const T xlo = S->xlo, xhi = S->xhi, cap = S->cap;
     const bool has_cap = S->has_cap != 0, pflag = S->pflag != 0;
     const bool pending = (flags & F_PENDING) != 0, ones = (flags & F_XONES) != 0;
+    const Region R = region_of<MK>(ctx, S);
     double gd = 0.0;
     auto pf = [&](int i) {
         In4<T> r; r.a = ld2(x, i); r.b = ld2(gr, i);
@@ -406,7 +457,8 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
         r.d = pflag ? ld2(Xbuf, i) : mk2((T)0, (T)0);
         return r;
     };
-    auto one = [&](T xv, T gv, T cv, T Xv, T& xo) -> T {
+    auto one = [&](bool m, T xv, T gv, T cv, T Xv, T& xo) -> T {
+        if (!m) { xo = (T)0; return (T)0; }
         T y;
         if (pflag) {
             y = proj_point(cv, Xv, lam_proj, has_cap, cap);
@@ -423,8 +475,8 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
     };
     auto pe = [&](int i, const In4<T>& in) -> V2<T> {
         V2<T> xo, d;
-        d.x = one(in.a.x, in.b.x, in.c.x, in.d.x, xo.x);
-        d.y = one(in.a.y, in.b.y, in.c.y, in.d.y, xo.y);
+        d.x = one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, in.d.x, xo.x);
+        d.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y, xo.y);
         if (!pflag && pending) st2(x, i, xo);
         st2(dbuf, i, d);
         return d;
@@ -434,19 +486,24 @@ template <typename T, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx, const I
 }
 
 // consumer of A(d): d_tf, first line-search trial (lam = 1) fused            sgp.py:326-334
-template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
-    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
+    const Region R = region_of<MK>(ctx, S);
     KSum acc[3];
     acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto cf = [&](int i) { In3<T> r; r.a = ld2(xtf, i); r.b = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.c = ld2(gn, i); return r; };
+    auto one = [&](bool m, T xtfv, T bk, T gnv, T v, T& dt, T& p) {
+        if (!m) { dt = (T)0; p = (T)0; return; }
+        dt = MK ? ndiv(v, div) : v;
+        const T xt = nadd(xtfv, dt);                       // lam = 1
+        p = objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+    };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
-        st2(dtf, i, v);
-        V2<T> p;
-        const T xt0 = nadd(in.a.x, v.x);                   // lam = 1
-        p.x = objective_pixel(dk, in.c.x, nadd(xt0, in.b.x), xt0, want_s1 != 0, acc);
-        const T xt1 = nadd(in.a.y, v.y);
-        p.y = objective_pixel(dk, in.c.y, nadd(xt1, in.b.y), xt1, want_s1 != 0, acc);
+        V2<T> dt, p;
+        one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, v.x, dt.x, p.x);
+        one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, v.y, dt.y, p.y);
+        st2(dtf, i, dt);
         st2(t1, i, p);
     };
     conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
@@ -455,38 +512,43 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const Img
 }
 
 // slab part of sum dD_beta/dbeta at the rejected trial point               sgp.py:798-800
-template <typename T, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx, const ImgState<T>* S, T lam, T b) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx, const ImgState<T>* S, T lam, T b) {
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    const Region R = region_of<MK>(ctx, S);
     double db = 0.0;
     auto fetch = [&](int i) {
         In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
     };
-    auto body = [&](int, const In4<T>& in) {
-        db += (double)dbeta_pixel(in.d.x, nadd(nadd(in.a.x, nmul(lam, in.b.x)), in.c.x), b);
-        db += (double)dbeta_pixel(in.d.y, nadd(nadd(in.a.y, nmul(lam, in.b.y)), in.c.y), b);
+    auto body = [&](int i, const In4<T>& in) {
+        if (inside<MK>(R, i)) db += (double)dbeta_pixel(in.d.x, nadd(nadd(in.a.x, nmul(lam, in.b.x)), in.c.x), b);
+        if (inside<MK>(R, i + 1)) db += (double)dbeta_pixel(in.d.y, nadd(nadd(in.a.y, nmul(lam, in.b.y)), in.c.y), b);
     };
     pair_loop<1>(ctx, S->nslab, fetch, body);
     return db;
 }
 
 // one more line-search trial: objective at x_tf + lam d_tf                  sgp.py:329-334
-template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk, int want_s1) {
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
+    const Region R = region_of<MK>(ctx, S);
     KSum acc[3];
     acc[0].clear(); acc[1].clear(); acc[2].clear();
     auto fetch = [&](int i) {
         In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
     };
+    auto one = [&](bool m, T xtfv, T dtfv, T bk, T gnv) -> T {
+        if (!m) return (T)0;
+        const T xt = nadd(xtfv, nmul(lam, dtfv));
+        return objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+    };
     auto body = [&](int i, const In4<T>& in) {
         V2<T> p;
-        const T xt0 = nadd(in.a.x, nmul(lam, in.b.x));
-        p.x = objective_pixel(dk, in.d.x, nadd(xt0, in.c.x), xt0, want_s1 != 0, acc);
-        const T xt1 = nadd(in.a.y, nmul(lam, in.b.y));
-        p.y = objective_pixel(dk, in.d.y, nadd(xt1, in.c.y), xt1, want_s1 != 0, acc);
+        p.x = one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, in.d.x);
+        p.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y);
         st2(t1, i, p);
     };
     pair_loop<2>(ctx, S->nslab, fetch, body);
@@ -495,10 +557,11 @@ template <typename T, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgSta
 }
 
 // consumer of A^T(.): new gradient, y_k, Barzilai-Borwein sums, stop-rule / error sums   sgp.py:343-365, 394-402
-template <typename T, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgState<T>* S, T lam, int kind) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgState<T>* S, T lam, int kind) {
     const T* t1 = S->t1; T* gr = S->g; const T* dbuf = S->d; const T* x = S->x; const T* truth = S->truth;
-    const T xlo = S->xlo, xhi = S->xhi, scaling = S->scaling;
+    const T xlo = S->xlo, xhi = S->xhi, scaling = S->scaling, div = S->div_at;
     const bool want_err = S->want_err != 0, stop2 = S->stop2 != 0;
+    const Region R = region_of<MK>(ctx, S);
     double bb[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) bb[k] = 0.0;
@@ -506,7 +569,9 @@ template <typename T, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgSta
         In5<T> r; r.a = ld2(t1, i); r.b = ld2(gr, i); r.c = ld2(dbuf, i); r.d = ld2(x, i);
         r.e = want_err ? ld2(truth, i) : mk2((T)0, (T)0); return r;
     };
-    auto one = [&](T p1, T gold, T dv, T xv, T tr, T w) -> T {
+    auto one = [&](bool m, T p1, T gold, T dv, T xv, T tr, T w) -> T {
+        if (!m) return (T)0;
+        if (MK) w = ndiv(w, div);
         const T gnew = (kind == 0) ? nsub((T)1, w) : nsub(p1, w);
         const T yk = nsub(gnew, gold);
         const T sk = nmul(lam, dv);
@@ -524,8 +589,8 @@ template <typename T, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, const ImgSta
     };
     auto ca = [&](int i, const In5<T>& in, V2<T> w) {
         V2<T> gnew;
-        gnew.x = one(in.a.x, in.b.x, in.c.x, in.d.x, in.e.x, w.x);
-        gnew.y = one(in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
+        gnew.x = one(inside<MK>(R, i), in.a.x, in.b.x, in.c.x, in.d.x, in.e.x, w.x);
+        gnew.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
         st2(gr, i, gnew);
     };
     conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
@@ -554,12 +619,16 @@ template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgSt
 // -------------------------------------------------------------------------------------------------
 // the controller
 // -------------------------------------------------------------------------------------------------
-template <typename T, class Ctx>
-BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* const* buf, cplx<T>* tf, int img) {
+template <typename T, bool MK, class Ctx>
+BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* const* buf, cplx<T>* tf, cplx<T>* tf_adj, int img) {
     const bsgp_params& P = a.p;
     const int nslab = a.g.rows_per_cta * a.g.nx;
     const size_t npix = (size_t)a.g.ny * a.g.nx;
-    const double npix_d = (double)npix;
+    constexpr bool masked = MK;                                          // zero-padded operator: the image is a window of the grid
+    const double npix_d = masked ? (double)(P.region[1] - P.region[0]) * (double)(P.region[3] - P.region[2]) : (double)npix;
+    // A^T: conj(TF) of the same PSF (sgp.py:110), or the spectrum of a second kernel, psf.conj().T (sgp.py:157)
+    cplx<T>* tf_at = P.adjoint_second_psf ? tf_adj : tf;
+    const int mode_at = P.adjoint_second_psf ? CONV_TF : CONV_CTF;
     const size_t goff = (size_t)img * npix + (size_t)ctx.rank * nslab;
     const size_t toff = (size_t)img * (P.maxit + 1);
     const bool leader = (ctx.rank == 0 && ctx.tid == 0);
@@ -583,11 +652,13 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         S->nslab = nslab; S->bkg_img = bkg_img; S->init_recon = P.init_recon; S->has_cap = P.has_sat != 0;
         S->pflag = pflag; S->want_err = want_err; S->stop2 = (P.stop_criterion == 2);
         S->bkg_raw_s = bkg_raw_s;
+        S->masked = masked; S->reg[0] = P.region[0]; S->reg[1] = P.region[1]; S->reg[2] = P.region[2]; S->reg[3] = P.region[3];
+        S->div_a = masked ? (T)P.div_a : (T)1; S->div_at = masked ? (T)P.div_at : (T)1;
     }
 
     // ------------------------------------------------------------------ setup (sgp.py:166-217)
     double v3[3];
-    const R3 st = ph_stats<T>(ctx, S);
+    const R3 st = ph_stats<T, MK>(ctx, S);
     v3[0] = st.a; v3[1] = st.b;
     double mx = st.c;
     ctx.allreduce_sum(v3, 2);
@@ -597,7 +668,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
     const T bkg_s = ndiv(bkg_raw_s, scaling);
     if (ctx.tid == 0) { S->scaling = scaling; S->bkg_s = bkg_s; }
 
-    double vmin = ph_scale_gn<T>(ctx, S);
+    double vmin = ph_scale_gn<T, MK>(ctx, S);
     ctx.allreduce_min(vmin);
     const T eps = Eps<T>::v();
     const double flux_in = P.has_flux ? a.flux[img] : 0.0;
@@ -608,7 +679,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         S->cap = has_cap ? nsub(ndiv((T)P.ccd_sat_level, scaling), eps) : (T)0;
         S->xlo = (T)0; S->xhi = (T)0;
     }
-    v3[0] = ph_init<T>(ctx, S);
+    v3[0] = ph_init<T, MK>(ctx, S);
     ctx.allreduce_sum(v3, 1);
     const double flux = P.has_flux ? ndiv(flux_in, (double)scaling) : v3[0];
 
@@ -630,7 +701,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             if (lam == 1.0) return pre[1] - flux;
             if (lam == -1.0) return pre[2] - flux;
         }
-        double s = ph_proj_eval<T>(ctx, S, (T)lam);
+        double s = ph_proj_eval<T, MK>(ctx, S, (T)lam);
         ctx.allreduce_sum(&s, 1);
         return s - flux;
     };
@@ -642,13 +713,13 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
             total_evals += pr.evals;
             if (pr.status != PROJ_OK) status = BSGP_ST_PROJ_NO_BRACKET;
-            ph_proj_init_store<T>(ctx, S, (T)pr.lambda);
+            ph_proj_init_store<T, MK>(ctx, S, (T)pr.lambda);
         }
     }
 
     double truth_sq = 1.0;
     if (want_err && status == BSGP_ST_OK) {                             // :240-244, 255-257
-        const R2 e = ph_err0<T>(ctx, S);
+        const R2 e = ph_err0<T, MK>(ctx, S);
         double e2[2] = {e.a, e.b};
         ctx.allreduce_sum(e2, 2);
         truth_sq = e2[1];
@@ -667,20 +738,20 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         ph_rf_copy<T>(ctx, S, 0);
         conv_middle<T>(ctx, S, tf, CONV_TF);
         {
-            const R3 o = ph_ri_obj0<T>(ctx, S, dk, !s1_valid);
+            const R3 o = ph_ri_obj0<T, MK>(ctx, S, dk, !s1_valid);
             acc[0] = o.a; acc[1] = o.b; acc[2] = o.c;
         }
         ctx.allreduce_sum(acc, 3);
         if (dk.kind == 1) { s1 = acc[0]; s1_valid = true; }
         fv = objective_value(dk, acc, s1, flux, npix_d);
         // ---------------------------------------------------------------- gradient
-        ph_rf_grad<T>(ctx, S, dk.kind, (T)0, F_FIRST);
-        conv_middle<T>(ctx, S, tf, CONV_CTF);
-        ph_ri_grad0<T>(ctx, S, dk.kind);
+        ph_rf_grad<T, MK>(ctx, S, dk.kind, (T)0, F_FIRST);
+        conv_middle<T>(ctx, S, tf_at, mode_at);
+        ph_ri_grad0<T, MK>(ctx, S, dk.kind);
         // ---------------------------------------------------------------- scaling-matrix bounds (:268-273)
         ph_rf_copy<T>(ctx, S, 1);
-        conv_middle<T>(ctx, S, tf, CONV_CTF);
-        const R2 lh = ph_ri_bounds<T>(ctx, S, flux);
+        conv_middle<T>(ctx, S, tf_at, mode_at);
+        const R2 lh = ph_ri_bounds<T, MK>(ctx, S, flux);
         double lo = lh.a, hi = lh.b;
         ctx.allreduce_min(lo);
         ctx.allreduce_max(hi);
@@ -724,7 +795,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         T lam_proj = (T)0;
         if (pflag) {
             {
-                const R3 t = ph_trial_point<T>(ctx, S, al, lam_pending, flags);
+                const R3 t = ph_trial_point<T, MK>(ctx, S, al, lam_pending, flags);
                 pre[0] = t.a; pre[1] = t.b; pre[2] = t.c;
                 ctx.allreduce_sum(pre, 3);
                 have_pre = true;
@@ -741,11 +812,11 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         // ---- d = y - x, gd = d.g, d_tf = A(d) with the first line-search trial fused (:318-334)
         double sums[4];   // [0..2] objective terms, [3] gd
         double lam = 1.0;
-        sums[3] = ph_rf_dir<T>(ctx, S, al, lam_proj, lam_pending, flags);
+        sums[3] = ph_rf_dir<T, MK>(ctx, S, al, lam_proj, lam_pending, flags);
         pending = false;
         conv_middle<T>(ctx, S, tf, CONV_TF);
         {
-            const R3 o = ph_ri_trial<T>(ctx, S, dk, !s1_valid);
+            const R3 o = ph_ri_trial<T, MK>(ctx, S, dk, !s1_valid);
             sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
         }
         ctx.allreduce_sum(sums, 4);
@@ -758,7 +829,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         // ---- backtracking (:328-349 / :776-800): accept iff fv <= fr + gamma*lam*gd or lam < 1e-12
         while (!(fv <= nadd(f_ref, nmul(nmul(P.gamma, lam), gd)) || lam < 1e-12)) {
             if (is_beta && P.adapt_beta && dk.kind == 1) {               // :798-800, den of the rejected trial
-                double db = ph_dbeta<T>(ctx, S, (T)lam, dk.b);
+                double db = ph_dbeta<T, MK>(ctx, S, (T)lam, dk.b);
                 ctx.allreduce_sum(&db, 1);
                 beta_p = nsub(beta_p, nmul(lr, db / npix_d));
                 dk = make_divk<T>(P.divergence, beta_p);
@@ -766,7 +837,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             }
             lam = nmul(lam, P.ls_beta);
             ++trials;
-            const R3 o = ph_trial<T>(ctx, S, (T)lam, dk, !s1_valid);
+            const R3 o = ph_trial<T, MK>(ctx, S, (T)lam, dk, !s1_valid);
             sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             ctx.allreduce_sum(sums, 3);
             if (dk.kind == 1 && !s1_valid) { s1 = sums[0]; s1_valid = true; }
@@ -775,9 +846,9 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         total_trials += trials;
 
         // ---- accept: x_tf, new gradient through A^T, BB sums (:337-347, 355-365, 402); x itself is updated lazily
-        ph_rf_grad<T>(ctx, S, dk.kind, (T)lam, 0);
-        conv_middle<T>(ctx, S, tf, CONV_CTF);
-        R7 bbr = ph_ri_bb<T>(ctx, S, (T)lam, dk.kind);
+        ph_rf_grad<T, MK>(ctx, S, dk.kind, (T)lam, 0);
+        conv_middle<T>(ctx, S, tf_at, mode_at);
+        R7 bbr = ph_ri_bb<T, MK>(ctx, S, (T)lam, dk.kind);
         double* bb = bbr.v;
         ctx.allreduce_sum(bb, 7);
         X_is_ones = false;

@@ -21,7 +21,7 @@ from ._capi import BsgpError, DIV_BETA, DIV_KL, check, lib
 _NP = {"float64": np.float64, "float32": np.float32}
 _DT = {"float64": _capi.BSGP_F64, "float32": _capi.BSGP_F32}
 
-_SOLVER_KEYS = ("init_recon", "proj_type", "stop_criterion", "MAXIT", "gamma", "beta", "alpha", "alpha_min", "alpha_max",
+_SOLVER_KEYS = ("region", "div_a", "div_at", "adjoint_second_psf", "init_recon", "proj_type", "stop_criterion", "MAXIT", "gamma", "beta", "alpha", "alpha_min", "alpha_max",
                 "M_alpha", "tau", "M", "max_projs", "verbose", "ccd_sat_level", "scale_data", "errflag",
                 "tol_convergence", "adapt_beta", "lr", "lr_exp_param", "schedule_lr")
 
@@ -62,6 +62,15 @@ class Plan:
             raise ValueError(f"PSF shape {a.shape[-2:]} must equal the image shape {(self.ny, self.nx)} "
                              "(the reference's numpy A/AT closure has the same requirement, sgp.py:108-120)")
         check(lib().bsgp_set_psf_host(self._h, a.ctypes.data, n))
+        return n
+
+    def set_psf_adjoint(self, psf):
+        """Second kernel, used for A^T by the zero-padded operator (sgp.py:157); numpy [ny,nx] / [n,ny,nx]."""
+        a = np.ascontiguousarray(psf, dtype=_NP[self.dtype])
+        n = 1 if a.ndim == 2 else a.shape[0]
+        if a.shape[-2:] != (self.ny, self.nx):
+            raise ValueError("adjoint kernel must be embedded in the plan's grid")
+        check(lib().bsgp_set_psf_adjoint_host(self._h, a.ctypes.data, n))
         return n
 
     def apply_psf(self, x, adjoint=False):
@@ -137,6 +146,36 @@ def _queue_order(divergence, beta0):
     return np.ascontiguousarray(np.argsort(np.abs(beta0 - 1.0), kind="stable").astype(np.int32))
 
 
+class PaddedGeometry:
+    """Placement of an ny x nx image and a ky x kx kernel on the square power-of-two grid that
+    astropy.convolution.convolve_fft uses with boundary='fill' (fft_pad = psf_pad = True): side
+    2^ceil(log2(max(image + kernel shape))), both centred (sgp.py:138,157 call it with the defaults)."""
+
+    def __init__(self, ny, nx, ky, kx):
+        self.ny, self.nx, self.ky, self.kx = ny, nx, ky, kx
+        self.P = int(2 ** np.ceil(np.log2(max(ny + ky, nx + kx))))
+        c = self.P - (self.P + 1) // 2
+        self.rows = slice(c - ny // 2, c + (ny + 1) // 2)
+        self.cols = slice(c - nx // 2, c + (nx + 1) // 2)
+        self.c = c
+        self.region = (self.rows.start, self.rows.stop, self.cols.start, self.cols.stop)
+
+    def embed(self, a, dtype):
+        """[B,ny,nx] -> [B,P,P], zeros in the padding."""
+        out = np.zeros(a.shape[:-2] + (self.P, self.P), dtype=dtype)
+        out[..., self.rows, self.cols] = a
+        return out
+
+    def kernel(self, k, dtype):
+        """Normalised kernel(s) [.., kh, kw] centred on the grid; returns (grid array, weight constant)."""
+        k = np.asarray(k, dtype=np.float64)
+        kh, kw = k.shape[-2:]
+        k = k / k.sum(axis=(-2, -1), keepdims=True)
+        out = np.zeros(k.shape[:-2] + (self.P, self.P), dtype=dtype)
+        out[..., self.c - kh // 2:self.c + (kh + 1) // 2, self.c - kw // 2:self.c + (kw + 1) // 2] = k
+        return out, float(out.reshape(-1, self.P * self.P)[0].sum())
+
+
 def _params(divergence, kw, has_flux):
     unknown = set(kw) - set(_SOLVER_KEYS)
     if unknown:
@@ -145,15 +184,18 @@ def _params(divergence, kw, has_flux):
 
 
 def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=None, obj=None, dtype="float64",
-                device=0, trace=False, plan=None, psf_is_set=False, **kw):
+                device=0, trace=False, plan=None, psf_is_set=False, padded=False, **kw):
     """Restore a batch of independent images in one persistent kernel launch.
 
     gn [B,ny,nx]; psf [ny,nx] (shared) or [B,ny,nx]; bkg scalar, [B] or [B,ny,nx]; flux None or [B];
     betaParam scalar or [B].  Keyword arguments are those of sgp()/sgp_betaDiv() (sgp.py:41-47,
     506-513).  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (asynchronous on the
-    current stream)."""
+    current stream).  ``padded=True`` selects the zero-padded operator of use_original_SGP_Afunction=False
+    (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size, numpy inputs only."""
     if divergence not in ("kl", "beta"):
         raise ValueError("divergence must be 'kl' or 'beta'")
+    if padded:
+        return _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw)
     if _is_tensor(gn):
         return _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw)
     npdt = _NP[dtype]
@@ -202,6 +244,35 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
                        ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
     check(lib().bsgp_solve_batch_host(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co)))
     return BatchResult(trace=tr, **out)
+
+
+def _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw):
+    """Embed into the padded grid, solve there with the window mask, crop (see PaddedGeometry)."""
+    if _is_tensor(gn):
+        raise NotImplementedError("padded=True takes numpy inputs")
+    npdt = _NP[dtype]
+    gn = np.asarray(gn, dtype=npdt)
+    psf = np.asarray(psf, dtype=np.float64)
+    if gn.ndim != 3:
+        raise ValueError("gn must be [batch, ny, nx]")
+    B, ny, nx = gn.shape
+    geo = PaddedGeometry(ny, nx, psf.shape[-2], psf.shape[-1])
+    if geo.P > 8192:
+        raise ValueError(f"padded grid {geo.P} exceeds the largest supported side (8192)")
+    plan = get_plan(geo.P, geo.P, dtype, device)
+    big, div_a = geo.kernel(psf, npdt)
+    bigt, div_at = geo.kernel(np.conj(np.swapaxes(psf, -1, -2)), npdt)          # psf.conj().T, sgp.py:157
+    if plan.set_psf(big) not in (1, B) or plan.set_psf_adjoint(bigt) not in (1, B):
+        raise ValueError("psf must be one kernel or one per batch entry")
+    bkg = np.asarray(bkg, dtype=npdt)
+    bkg_p = geo.embed(bkg, npdt) if bkg.ndim == 3 else bkg
+    res = solve_batch(geo.embed(gn, npdt), None, bkg_p, divergence=divergence, flux=flux, betaParam=betaParam,
+                      x0=None if x0 is None else geo.embed(np.asarray(x0, dtype=npdt), npdt),
+                      obj=None if obj is None else geo.embed(np.asarray(obj, dtype=npdt), npdt), dtype=dtype, device=device,
+                      trace=trace, plan=plan, psf_is_set=True, region=geo.region, div_a=div_a, div_at=div_at,
+                      adjoint_second_psf=True, **kw)
+    res.x = np.ascontiguousarray(res.x[:, geo.rows, geo.cols])
+    return res
 
 
 def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw):

@@ -96,16 +96,13 @@ def _write_log(res, kw, tol):
 def _solve_one(divergence, gn, psf, bkg, kw, flux, betaParam, obj, save, use_original_SGP_Afunction):
     _check_psf(psf)
     logging.basicConfig(filename='sgp.log', level=logging.INFO, force=True)       # sgp.py:104 / 564
-    if not use_original_SGP_Afunction:
-        raise NotImplementedError("use_original_SGP_Afunction=False (astropy convolve_fft operator, sgp.py:121-161) "
-                                  "is not built yet; only the numpy circular-convolution operator is available")
     if save:
         raise NotImplementedError("save=True (per-iteration FITS dumps, sgp.py:223-231,416-422) is out of scope")
     gn = np.asarray(gn)
     psf = np.asarray(psf)
     if gn.ndim != 2:
         raise ValueError("gn must be a 2-D image")
-    if psf.shape != gn.shape:
+    if use_original_SGP_Afunction and psf.shape != gn.shape:
         # np.reshape(x, psf.shape) in the reference's closure fails the same way (sgp.py:112)
         raise ValueError(f"cannot reshape array of size {gn.size} into shape {psf.shape}")
     if kw["errflag"] and obj is None:
@@ -124,7 +121,7 @@ def _solve_one(divergence, gn, psf, bkg, kw, flux, betaParam, obj, save, use_ori
     res = engine.solve_batch(np.asarray(gn, dtype=np.float64)[None], psf, bkg_a, divergence=divergence,
                              flux=None if flux is None else [float(flux)], betaParam=float(betaParam), x0=x0,
                              obj=None if (obj is None or not kw["errflag"]) else np.asarray(obj, dtype=np.float64)[None],
-                             device=DEVICE, **kw)
+                             device=DEVICE, padded=not use_original_SGP_Afunction, **kw)
     status = int(res.status[0])
     if status != _capi.ST_OK:
         raise _status_error(status)

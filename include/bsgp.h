@@ -63,6 +63,14 @@ typedef struct bsgp_params {
     int adapt_beta;        /* beta-divergence only */
     double lr, lr_exp_param;
     int schedule_lr;
+    /* Zero-padded ("astropy") operator, use_original_SGP_Afunction=False (sgp.py:121-161, 583-615).  The caller
+     * embeds every image into the plan's power-of-two FFT grid; region = {r0, r1, c0, c1} is the window the image
+     * occupies ([r0, r1) x [c0, c1)).  All zeros: the image is the whole grid (circular operator).  Pixel counts,
+     * sums and the projection only see the window; operator outputs are divided by div_a (A) / div_at (A^T), the
+     * kernel-weight constants of convolve_fft's nan_treatment='interpolate'. */
+    int region[4];
+    double div_a, div_at;
+    int adjoint_second_psf;   /* A^T uses the spectrum set by bsgp_set_psf_adjoint (kernel psf.conj().T) instead of conj(TF) */
 } bsgp_params;
 
 typedef struct bsgp_inputs {
@@ -124,6 +132,9 @@ int bsgp_plan_configure(bsgp_plan* plan, int cluster_size, int threads);
  * the whole batch) or the batch size (one PSF per image). */
 int bsgp_set_psf(bsgp_plan* plan, const void* psf_dev, int n_psf, void* stream);
 int bsgp_set_psf_host(bsgp_plan* plan, const void* psf_host, int n_psf);
+/* Second kernel for A^T (sgp.py:157: convolve_fft(x, psf.conj().T, ...)); same n_psf as bsgp_set_psf. */
+int bsgp_set_psf_adjoint(bsgp_plan* plan, const void* psf_dev, int n_psf, void* stream);
+int bsgp_set_psf_adjoint_host(bsgp_plan* plan, const void* psf_host, int n_psf);
 
 /* The restoration loop for `batch` independent images; one persistent kernel launch, no host sync. */
 int bsgp_solve_batch(bsgp_plan* plan, const bsgp_params* params, int batch, const bsgp_inputs* in_dev,

@@ -86,6 +86,64 @@ class CircularPsf:
 
 
 # --------------------------------------------------------------------------
+# PSF operator, zero-padded FFT convolution (sgp.py:121-161 / 583-615)
+# --------------------------------------------------------------------------
+class PaddedPsf:
+    """``use_original_SGP_Afunction=False``: A(x) = convolve_fft(x, psf, normalize_kernel=True,
+    normalization_zero_tol=1e-4), A^T(x) = convolve_fft(x, psf.conj().T, ...) (sgp.py:138,157).
+
+    PARITY UNPINNED.  ``astropy.convolution.convolve_fft`` is a third-party function that is neither vendored
+    in the reference nor installed here (the reference pins no version), and no reference test exercises this
+    branch.  This class restates the function's published algorithm for the arguments the reference passes and
+    the remaining defaults (boundary='fill', fill_value=0.0, nan_treatment='interpolate', crop=True, and hence
+    psf_pad = fft_pad = True): kernel divided by its sum; image and kernel placed in the centre of a square
+    2^ceil(log2(max(image + kernel shape))) array (zeros elsewhere); kernel spectrum taken after ifftshift;
+    product of spectra; the interpolation weights ifftn(fftn(ones) * kernfft) divide the result inside the
+    image window; weights below 10 eps zero the result; the image window is cropped out."""
+
+    def __init__(self, psf, shape):
+        self.shape = tuple(shape)
+        self.fwd = self._prepare(np.asarray(psf))
+        self.adj = self._prepare(np.asarray(psf).conj().T)
+
+    def _prepare(self, kernel):
+        ksum = kernel.sum()
+        if abs(ksum) < 1e-4:
+            raise ValueError("The kernel can't be normalized, because its sum is close to zero.")
+        kern = kernel / ksum
+        fsize = int(2 ** np.ceil(np.log2(np.max(np.array(self.shape) + np.array(kern.shape)))))
+        newshape = (fsize, fsize)
+        aslc, kslc = [], []
+        for n, na, nk in zip(newshape, self.shape, kern.shape):
+            centre = n - (n + 1) // 2
+            aslc.append(slice(centre - na // 2, centre + (na + 1) // 2))
+            kslc.append(slice(centre - nk // 2, centre + (nk + 1) // 2))
+        aslc, kslc = tuple(aslc), tuple(kslc)
+        bigkernel = np.zeros(newshape, dtype=complex)
+        bigkernel[kslc] = kern
+        kernfft = np.fft.fftn(np.fft.ifftshift(bigkernel))
+        bigimwt = np.ones(newshape, dtype=complex)
+        wtsm = np.fft.ifftn(np.fft.fftn(bigimwt) * kernfft)
+        bigimwt[aslc] = wtsm.real[aslc]
+        return newshape, aslc, kernfft, bigimwt
+
+    def _apply(self, vec, prep):
+        newshape, aslc, kernfft, bigimwt = prep
+        big = np.zeros(newshape, dtype=complex)
+        big[aslc] = np.reshape(vec, self.shape)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rifft = np.fft.ifftn(np.fft.fftn(big) * kernfft) / bigimwt
+        rifft[bigimwt < 10 * np.finfo(bigimwt.dtype).eps] = 0.0
+        return rifft[aslc].real.ravel()
+
+    def forward(self, vec):
+        return self._apply(vec, self.fwd)
+
+    def adjoint(self, vec):
+        return self._apply(vec, self.adj)
+
+
+# --------------------------------------------------------------------------
 # flux-conserving projection (flux_conserve_proj.py:7-144)
 # --------------------------------------------------------------------------
 class _Clamp:
@@ -239,7 +297,7 @@ def solve(gn, psf, bkg, divergence="kl", init_recon=0, proj_type=0, stop_criteri
           gamma=1e-4, beta=0.4, alpha=1.3, alpha_min=1e-5, alpha_max=1e5, M_alpha=3, tau=0.5, M=1,
           max_projs=1000, obj=None, verbose=True, flux=None, ccd_sat_level=None, scale_data=True,
           errflag=False, adapt_beta=True, betaParam=1.005, lr=1e-3, lr_exp_param=0.1,
-          schedule_lr=False, tol_convergence=1e-4):
+          schedule_lr=False, tol_convergence=1e-4, use_original_SGP_Afunction=True):
     """One restoration.  ``divergence="kl"`` follows sgp.py:41-438, ``"beta"`` sgp.py:506-895
     (numpy A/A^T closure only).  Returns an OracleResult; ``(x, iters, discr, times, err)`` are
     what the reference returns."""
@@ -247,7 +305,7 @@ def solve(gn, psf, bkg, divergence="kl", init_recon=0, proj_type=0, stop_criteri
     if abs(np.sum(psf.flatten()) - 1.) > 1e4 * MACHINE_EPS:              # :98-102
         raise ValueError("PSF is not normalized! Provide a normalized PSF!")
     shape = gn.shape
-    op = CircularPsf(psf)
+    op = CircularPsf(psf) if use_original_SGP_Afunction else PaddedPsf(psf, shape)
     tr = Trace()
     lr0 = lr
     t0 = default_timer()

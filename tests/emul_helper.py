@@ -47,8 +47,9 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x0=None, **kw):
-    """Emulated solve of one image; keyword arguments as sgp()/sgp_betaDiv()."""
+def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x0=None, psf_adjoint=None, **kw):
+    """Emulated solve of one image; keyword arguments as sgp()/sgp_betaDiv() (+ region / div_a / div_at /
+    adjoint_second_psf with psf_adjoint for the zero-padded operator: inputs already embedded in the grid)."""
     L = lib()
     ny, nx = gn.shape
     gn = np.ascontiguousarray(gn, dtype=np.float64)
@@ -70,8 +71,9 @@ def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x
     tt = np.zeros(maxit + 1, np.int32); te = np.zeros(maxit + 1, np.int32)
     objc = None if obj is None else np.ascontiguousarray(obj, dtype=np.float64)
     x0c = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
-    L.emul_solve.argtypes = [C.c_int, C.c_int, C.POINTER(capi.Params)] + [C.c_void_p] * 2 + [C.c_void_p, C.c_int] + [C.c_void_p] * 19
-    rc = L.emul_solve(ny, nx, C.byref(p), _p(gn), _p(psf), _p(bkg), bkg_is_image, _p(fl), _p(b0), _p(x0c), _p(objc),
+    pa = None if psf_adjoint is None else np.ascontiguousarray(psf_adjoint, dtype=np.float64)
+    L.emul_solve.argtypes = [C.c_int, C.c_int, C.POINTER(capi.Params)] + [C.c_void_p] * 3 + [C.c_void_p, C.c_int] + [C.c_void_p] * 19
+    rc = L.emul_solve(ny, nx, C.byref(p), _p(gn), _p(psf), _p(pa), _p(bkg), bkg_is_image, _p(fl), _p(b0), _p(x0c), _p(objc),
                       _p(x), _p(iters), _p(status), _p(discr), _p(stopv), _p(err), _p(bfin), _p(pe), _p(lt), _p(sc),
                       _p(ta), _p(tl), _p(tb), _p(tt), _p(te))
     assert rc == 0

@@ -28,7 +28,7 @@ struct HostCtx {
 template <typename T> struct HostPlan {
     ConvGeom g;
     size_t ws_bytes;
-    std::vector<cplx<T>> twx, twy, spec, tf;
+    std::vector<cplx<T>> twx, twy, spec, tf, tf_adj;
     std::vector<unsigned char> arena;      // emulated dynamic shared memory: [position table][workspace]
     unsigned ws_off = 0, ppx_off = 0;
     void bind() { g_emul_smem = arena.data(); }
@@ -45,8 +45,10 @@ template <typename T> struct HostPlan {
         fill_pos_table(ctx, g.px, smem_at<unsigned short>(ppx_off));
         return true;
     }
-    void make_tf(const T* psf) {
+    void make_tf(const T* psf, std::vector<cplx<T>>* dst = nullptr) {
         const int ny = g.ny, nx = g.nx;
+        std::vector<cplx<T>>& out = dst ? *dst : tf;
+        out.assign((size_t)(g.hx + 1) * ny, cmake<T>(0, 0));
         for (int phase = 0; phase < 2; ++phase)
             for (int r = 0; r < g.G; ++r) {
                 HostCtx ctx; ctx.rank = r; ctx.G = g.G;
@@ -57,7 +59,7 @@ template <typename T> struct HostPlan {
                 };
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
                 if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), pf, pe);
-                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), tf.data(), CONV_MAKE_TF);
+                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), out.data(), CONV_MAKE_TF);
             }
     }
     void apply(const T* x, T* y, int adjoint) {
@@ -122,7 +124,7 @@ int emul_conv_f32(int ny, int nx, int G, long long ws_limit, const float* x, con
 }
 
 // full solver, one image, one emulated CTA
-int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, const double* psf, const double* bkg,
+int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, const double* psf, const double* psf_adj, const double* bkg,
                int bkg_is_image, const double* flux, const double* beta0, const double* x0, const double* obj,
                double* x_out, int* iters, int* status, double* discr, double* stop_value, double* err, double* beta_final,
                int* proj_evals, int* ls_trials, double* scalars, double* tr_alpha, double* tr_lambda, double* tr_beta,
@@ -130,6 +132,7 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     HostPlan<double> pl;
     if (!pl.init(ny, nx, 1, (size_t)1 << 30)) return 1;
     pl.make_tf(psf);
+    if (psf_adj) pl.make_tf(psf_adj, &pl.tf_adj);
     const size_t npix = (size_t)ny * nx;
     std::vector<double> work(NBUF * npix, 0.0), times(params->maxit + 1, 0.0);
     double* buf[NBUF];
@@ -138,7 +141,7 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     memset(&a, 0, sizeof(a));
     a.p = *params; a.g = pl.g; a.batch = 1;
     a.gn = gn; a.bkg = bkg; a.bkg_is_image = bkg_is_image; a.flux = flux; a.beta0 = beta0; a.x0 = x0; a.obj = obj;
-    a.twx = pl.twx.data(); a.twy = pl.twy.data(); a.tf = pl.tf.data(); a.n_psf = 1;
+    a.twx = pl.twx.data(); a.twy = pl.twy.data(); a.tf = pl.tf.data(); a.tf_adj = psf_adj ? pl.tf_adj.data() : nullptr; a.n_psf = 1;
     a.x_out = x_out; a.iters = iters; a.status = status; a.discr = discr; a.times = times.data();
     a.stop_value = stop_value; a.err = err; a.beta_final = beta_final; a.proj_evals = proj_evals; a.ls_trials = ls_trials;
     a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
@@ -148,7 +151,8 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     memset(&S, 0, sizeof(S));
     S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem;
     pl.bind();
-    solve_image<double>(ctx, a, &S, buf, pl.tf.data(), 0);
+    if (params->region[1] > params->region[0]) solve_image<double, true>(ctx, a, &S, buf, pl.tf.data(), psf_adj ? pl.tf_adj.data() : pl.tf.data(), 0);
+    else solve_image<double, false>(ctx, a, &S, buf, pl.tf.data(), psf_adj ? pl.tf_adj.data() : pl.tf.data(), 0);
     return 0;
 }
 

@@ -201,8 +201,6 @@ def test_dropin_entry_points(bs, get_case, golden, tmp_path, monkeypatch, capsys
         bs.sgp(gn, psf * 1.001, bkg, MAXIT=2)
     with pytest.raises(ValueError, match="errflag"):
         bs.sgp(gn, psf, bkg, MAXIT=2, errflag=True)
-    with pytest.raises(NotImplementedError):
-        bs.sgp(gn, psf, bkg, MAXIT=2, use_original_SGP_Afunction=False)
     with pytest.raises(ValueError):                                       # non-positive flux, proj_type 1
         bs.sgp_betaDiv(gn, psf, np.float64(1e9), proj_type=1, MAXIT=3)
 
@@ -355,3 +353,57 @@ def test_frame_mode_8192_properties(bs):
     assert abs(r.x[0].sum() - flux) <= 1e-9 * flux
     assert np.all(np.diff(r.discr[0, :4]) < 0)
     bs.clear_plans()
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-padded operator (use_original_SGP_Afunction=False, sgp.py:121-161); PARITY UNPINNED: the oracle restates
+# astropy.convolution.convolve_fft from its published algorithm (oracle.PaddedPsf), astropy itself is unavailable
+# ------------------------------------------------------------------------------------------------
+def _padded_inputs(bs, ny, nx, k, seed, nstars=40):
+    from oracle import sgp_oracle as orc
+    rng = np.random.default_rng(seed)
+    psf = bs.synth.moffat_psf(k, k, 3.5, axis_ratio=1.2, theta=0.4)
+    psf /= psf.sum()
+    truth = np.zeros((ny, nx))
+    truth[rng.integers(3, ny - 3, nstars), rng.integers(3, nx - 3, nstars)] = 10 ** rng.uniform(3, 4.8, nstars)
+    gn = rng.poisson(np.maximum(orc.PaddedPsf(psf, truth.shape).forward(truth.ravel()).reshape(ny, nx), 0) + 300.0).astype(float)
+    return orc, gn, psf
+
+
+def test_padded_operator_dropin_stamp(bs, tmp_path, monkeypatch, capsys):
+    """The paper's stamp shape: 31 x 31 image, 31 x 31 PSF, application parameters
+    (application_sgp_star_stamps.py:82-89) through the drop-in sgp_betaDiv(use_original_SGP_Afunction=False)."""
+    monkeypatch.chdir(tmp_path)
+    orc, gn, psf = _padded_inputs(bs, 31, 31, 31, 3, nstars=2)
+    flux = np.float64((gn - 300.0).sum())
+    kw = dict(bs.synth.STAMP_KWARGS, betaParam=1.0248357, flux=flux)
+    x, it, discr, times, err = bs.sgp_betaDiv(gn, psf, np.float64(300.0), use_original_SGP_Afunction=False, **kw)
+    o = orc.solve(gn, psf, np.float64(300.0), divergence="beta", use_original_SGP_Afunction=False, **kw)
+    assert x.shape == (31, 31) and it == o.iters
+    assert np.abs(discr - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    assert np.abs(x - o.x).max() <= 1e-8 * np.abs(o.x).max()
+    assert abs(x.sum() - flux) <= 1e-9 * flux
+
+
+def test_padded_operator_subframe(bs):
+    """The paper's sub-frame shape: 375 x 375 image, 31 x 31 PSF (application_sgp_subdivisions.py:84-91) -> 512 x 512
+    grid, 2-D background, five beta inits in one batch; KL as well."""
+    orc, gn, psf = _padded_inputs(bs, 375, 375, 31, 4, nstars=350)
+    yy, xx = np.mgrid[0:375, 0:375] / 375.0
+    bkg = 300.0 + 20.0 * xx - 10.0 * yy
+    flux = float((gn - bkg).sum())
+    betas = np.array(bs.synth.beta_inits())
+    kw = dict(bs.synth.TILE_KWARGS, MAXIT=12)
+    r = bs.sgp_betaDiv_batch(np.repeat(gn[None], 5, 0), psf, np.repeat(bkg[None], 5, 0), flux=np.full(5, flux), betaParam=betas,
+                             padded=True, **kw)
+    assert r.x.shape == (5, 375, 375) and np.all(r.status == 0)
+    for i in (0, 4):
+        o = orc.solve(gn, psf, bkg, divergence="beta", flux=np.float64(flux), betaParam=float(betas[i]),
+                      use_original_SGP_Afunction=False, **kw)
+        assert int(r.iters[i]) == o.iters
+        assert np.abs(r.discr[i, :o.iters + 1] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+        assert np.abs(r.x[i] - o.x).max() <= 1e-8 * np.abs(o.x).max()
+        assert abs(r.x[i].sum() - flux) <= 1e-9 * flux
+    x, it, discr, times, _ = bs.sgp(gn, psf, bkg, init_recon=2, stop_criterion=2, MAXIT=8, use_original_SGP_Afunction=False)
+    o = orc.solve(gn, psf, bkg, divergence="kl", init_recon=2, stop_criterion=2, MAXIT=8, use_original_SGP_Afunction=False)
+    assert it == o.iters and np.abs(x - o.x).max() <= 1e-8 * np.abs(o.x).max()

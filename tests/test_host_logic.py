@@ -183,3 +183,52 @@ def test_queue_order_hint():
     assert order[0] == 4 and np.all(np.diff(np.abs(b[order] - 1.0)) >= 0)
     assert pkg.engine._queue_order("kl", b) is None
     assert pkg.engine._queue_order("beta", np.full(5, 1.005)) is None
+
+
+def _padded_case(ny, nx, k, seed):
+    import importlib.util
+    import sys
+    from oracle import sgp_oracle as orc
+    if "bsgp_pkg_for_test" not in sys.modules:
+        spec = importlib.util.spec_from_file_location("bsgp_pkg_for_test", os.path.join(ROOT, "beta-sgp_b200", "__init__.py"),
+                                                      submodule_search_locations=[os.path.join(ROOT, "beta-sgp_b200")])
+        pkg = importlib.util.module_from_spec(spec)
+        sys.modules["bsgp_pkg_for_test"] = pkg
+        spec.loader.exec_module(pkg)
+    pkg = sys.modules["bsgp_pkg_for_test"]
+    rng = np.random.default_rng(seed)
+    psf = pkg.synth.moffat_psf(k, k, 3.0, axis_ratio=1.2, theta=0.4)
+    psf /= psf.sum()
+    truth = np.zeros((ny, nx))
+    truth[rng.integers(3, ny - 3, 12), rng.integers(3, nx - 3, 12)] = 10 ** rng.uniform(3, 4.5, 12)
+    gn = rng.poisson(np.maximum(orc.PaddedPsf(psf, truth.shape).forward(truth.ravel()).reshape(ny, nx), 0) + 100.0).astype(float)
+    return pkg, orc, gn, psf
+
+
+@pytest.mark.parametrize("div,kw", [
+    ("beta", dict(proj_type=1, init_recon=2, stop_criterion=3, MAXIT=40, alpha=10.0, ccd_sat_level=65000, adapt_beta=True,
+                  schedule_lr=True, betaParam=1.02)),
+    ("kl", dict(init_recon=3, stop_criterion=2, MAXIT=25)),
+])
+def test_emulated_padded_operator_matches_oracle(div, kw):
+    """use_original_SGP_Afunction=False (sgp.py:121-161): odd-sized image (41 x 37), 15 x 15 asymmetric kernel, 64 x 64
+    grid.  The device headers (host emulation) against the oracle's restatement of convolve_fft (PARITY UNPINNED:
+    astropy itself is not available, see oracle.PaddedPsf)."""
+    pkg, orc, gn, psf = _padded_case(41, 37, 15, 0)
+    kw = dict(kw)
+    b0 = kw.pop("betaParam", 1.005)
+    flux = float((gn - 100.0).sum())
+    o = orc.solve(gn, psf, np.float64(100.0), divergence=div, betaParam=b0, flux=np.float64(flux), use_original_SGP_Afunction=False, **kw)
+    geo = pkg.engine.PaddedGeometry(41, 37, 15, 15)
+    assert geo.P == 64 and geo.region == (12, 53, 14, 51)
+    big, da = geo.kernel(psf, np.float64)
+    bigt, dat = geo.kernel(psf.conj().T, np.float64)
+    r = eh.solve(geo.embed(gn, np.float64), big, np.float64(100.0), divergence=div, betaParam=b0, flux=flux, psf_adjoint=bigt,
+                 region=geo.region, div_a=da, div_at=dat, adjoint_second_psf=True, **kw)
+    assert r["status"] == 0 and r["iters"] == o.iters
+    assert np.abs(r["discr"] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    x = r["x"][geo.rows, geo.cols]
+    assert np.abs(x - o.x).max() <= 1e-8 * np.abs(o.x).max()
+    pad = r["x"].copy()
+    pad[geo.rows, geo.cols] = 0.0
+    assert not pad.any()                                      # nothing leaks into the padding
