@@ -8,7 +8,7 @@
 //                  transformed by one complex FFT (row 2p -> real part, row 2p+1 -> imaginary
 //                  part) and untangled into two half spectra.  Values come from a producer functor
 //                  (so the elementwise step that creates the input is fused in) and the half
-//                  spectra go to the cluster's global (L2-resident) exchange buffer
+//                  spectra go to the cluster's exchange buffer in global memory
 //                  spec[ny][hx], hx = nx/2; column 0 packs the two real columns kx = 0 and
 //                  kx = nx/2 as (re, im).
 //   cols         : CTA `rank` owns packed spectrum columns [rank*hx/G, (rank+1)*hx/G): forward

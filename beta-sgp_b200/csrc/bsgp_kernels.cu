@@ -10,8 +10,9 @@
 //   * Scalars travel between the CTAs of a cluster through distributed shared memory
 //     (bsgp_device.cuh).
 //   * Per-image state that does not fit in shared memory lives in a per-CLUSTER scratch area (not
-//     per image): with ~15 clusters in flight the whole working set stays resident in the 126 MB L2,
-//     HBM only sees each input once and each output once.
+//     per image) in global memory.  Big slabs run as 4 small CTAs of different images per SM (71 clusters
+//     in flight for 256x256), so that scratch streams through L2 / HBM; stamps keep everything in shared
+//     memory.  Images of a megapixel or more use frame mode: one image over the whole (cooperative) grid.
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>

@@ -7,9 +7,9 @@ works with this directory on ``sys.path`` exactly as it does with the reference'
 argument meaning, return values, exceptions and side effects (``./sgp.log``, the two ``print`` lines
 of ``sgp_betaDiv``) follow sgp.py:41-47 / 506-513 / 438 / 895.  All arithmetic runs on the GPU
 (libbsgp.so); this file only validates arguments, moves arrays and reproduces the host-side side
-effects after the solve.  Not supported (raise NotImplementedError): ``save=True`` (per-iteration
-FITS dumps through astropy) and ``use_original_SGP_Afunction=False`` (astropy ``convolve_fft``;
-SURVEY.md §8f rank 1).
+effects after the solve.  ``use_original_SGP_Afunction=False`` selects the zero-padded operator with
+astropy ``convolve_fft`` semantics (sgp.py:121-161; any image / kernel size; parity unpinned).
+Not supported (raises NotImplementedError): ``save=True`` (per-iteration FITS dumps through astropy).
 """
 from __future__ import annotations
 
