@@ -49,3 +49,39 @@ def gather_to_all(local, n_items, rank, world_size, group=None):
             full[idx] = parts[r][:counts[r]]
         out[name] = full
     return out
+
+
+def solve_batch_sharded(gn, psf, bkg, flux=None, betaParam=1.005, group=None, device=None, **kw):
+    """Every rank passes the FULL batch (numpy arrays) and gets the full result back: rank r restores the images
+    shard_indices(B, r, W) on its own GPU (engine.solve_batch, one persistent kernel launch) and the per-image
+    results are all-gathered (NCCL when the process group is NCCL, gloo otherwise).  No data-path collective:
+    the images are independent problems (application_sgp_star_stamps.py:56-105, application_sgp_subdivisions.py:83-107).
+
+    psf: [ny,nx] shared or [B,ny,nx]; bkg: scalar, [B] or [B,ny,nx]; flux / betaParam: scalar or [B]."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if device is None:
+        device = int(__import__("os").environ.get("LOCAL_RANK", rank))
+    gn = np.asarray(gn)
+    B = gn.shape[0]
+    idx = shard_indices(B, rank, world)
+
+    def take(a, per_image_ndim):
+        a = np.asarray(a)
+        return a[idx] if a.ndim == per_image_ndim + 1 and a.shape[0] == B else a
+
+    psf = np.asarray(psf)
+    flux_l = None if flux is None else np.broadcast_to(np.asarray(flux, dtype=np.float64).reshape(-1), (B,))[idx]
+    beta_l = np.broadcast_to(np.asarray(betaParam, dtype=np.float64).reshape(-1), (B,))[idx]
+    bkg = np.asarray(bkg)
+    bkg_l = bkg[idx] if bkg.ndim >= 1 and bkg.shape[0] == B and bkg.size > 1 else bkg
+    r = engine.solve_batch(gn[idx], psf[idx] if psf.ndim == 3 else psf, bkg_l, flux=flux_l, betaParam=beta_l, device=device, **kw)
+    use_cuda = dist.is_initialized() and dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", device) if use_cuda else torch.device("cpu")
+    local = {k: torch.as_tensor(np.ascontiguousarray(getattr(r, k))).to(dev)
+             for k in ("x", "iters", "status", "discr", "times", "beta_final", "proj_evals", "ls_trials")}
+    full = gather_to_all(local, B, rank, world, group=group)
+    return {k: v.cpu().numpy() for k, v in full.items()}

@@ -407,3 +407,16 @@ def test_padded_operator_subframe(bs):
     x, it, discr, times, _ = bs.sgp(gn, psf, bkg, init_recon=2, stop_criterion=2, MAXIT=8, use_original_SGP_Afunction=False)
     o = orc.solve(gn, psf, bkg, divergence="kl", init_recon=2, stop_criterion=2, MAXIT=8, use_original_SGP_Afunction=False)
     assert it == o.iters and np.abs(x - o.x).max() <= 1e-8 * np.abs(o.x).max()
+
+
+def test_sharded_front_end_single_rank(bs, fixtures, golden):
+    """solve_batch_sharded without a process group (world size 1) equals solve_batch; the 2-rank gather is covered
+    by tests/test_sharding.py (gloo) and by tools/two_gpu_check.py on a 2-GPU box."""
+    gn = np.stack([fixtures[f"stamp{i}/gn"] for i in range(8)])
+    psf = np.stack([fixtures[f"stamp{i}/psf"] for i in range(8)])
+    bkg = np.array([float(fixtures[f"stamp{i}/bkg"]) for i in range(8)])
+    flux = np.array([float(golden[f"stamp{i:02d}/flux_in"]) for i in range(8)])
+    b0 = np.array([float(golden[f"stamp{i:02d}/beta0"]) for i in range(8)])
+    a = bs.sgp_betaDiv_batch(gn, psf, bkg, flux=flux, betaParam=b0, **bs.synth.STAMP_KWARGS)
+    s = bs.solve_batch_sharded(gn, psf, bkg, flux=flux, betaParam=b0, divergence="beta", **bs.synth.STAMP_KWARGS)
+    assert np.array_equal(s["x"], a.x) and np.array_equal(s["iters"], a.iters)
