@@ -420,3 +420,34 @@ def test_sharded_front_end_single_rank(bs, fixtures, golden):
     a = bs.sgp_betaDiv_batch(gn, psf, bkg, flux=flux, betaParam=b0, **bs.synth.STAMP_KWARGS)
     s = bs.solve_batch_sharded(gn, psf, bkg, flux=flux, betaParam=b0, divergence="beta", **bs.synth.STAMP_KWARGS)
     assert np.array_equal(s["x"], a.x) and np.array_equal(s["iters"], a.iters)
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (128, 32)])
+def test_non_square_images_against_oracle(bs, shape):
+    """Rectangular power-of-two images (row and column transforms of different length, uneven cluster split):
+    KL with a uint8 scalar background as loadmat delivers it (simulation_test_sgp.py:22) and beta-SGP with the
+    flux projection and a 2-D background."""
+    from oracle import sgp_oracle as orc
+    ny, nx = shape
+    rng = np.random.default_rng(ny + nx)
+    psf = bs.synth.moffat_psf(ny, nx, 3.0, axis_ratio=1.3, theta=0.7)
+    psf /= psf.sum()
+    truth = np.zeros(shape)
+    truth[rng.integers(0, ny, 25), rng.integers(0, nx, 25)] = 10 ** rng.uniform(2.5, 4.5, 25)
+    blur = np.real(np.fft.ifftn(np.fft.fftn(np.fft.fftshift(psf)) * np.fft.fftn(truth)))
+    gn = rng.poisson(np.maximum(blur, 0) + 7.0).astype(float)
+    x, it, discr, times, _ = bs.sgp(gn, psf, np.uint8(7), init_recon=3, stop_criterion=1, MAXIT=20)
+    o = orc.solve(gn, psf, np.uint8(7), divergence="kl", init_recon=3, stop_criterion=1, MAXIT=20)
+    assert it == o.iters == 20
+    assert np.abs(discr - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    assert np.abs(x - o.x).max() <= 1e-8 * np.abs(o.x).max()
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    bkg = 7.0 + 0.01 * xx + 0.02 * yy
+    gn2 = rng.poisson(np.maximum(blur, 0) + bkg).astype(float)
+    flux = np.float64((gn2 - bkg).sum())
+    kw = dict(bs.synth.TILE_KWARGS, MAXIT=25, flux=flux, betaParam=1.0248357)
+    r = bs.sgp_betaDiv_batch(gn2[None], psf, bkg[None], flux=[float(flux)], betaParam=1.0248357, **bs.synth.TILE_KWARGS | dict(MAXIT=25))
+    o = orc.solve(gn2, psf, bkg, divergence="beta", **kw)
+    assert int(r.iters[0]) == o.iters
+    assert np.abs(r.discr[0, :o.iters + 1] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    assert np.abs(r.x[0] - o.x).max() <= 1e-8 * np.abs(o.x).max()
