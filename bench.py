@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # the CPU arm runs one single-threaded numpy process per core; stop BLAS / OpenMP from oversubscribing them
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(_v, "1")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
