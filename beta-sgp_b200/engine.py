@@ -65,7 +65,13 @@ class Plan:
         return n
 
     def set_psf_adjoint(self, psf):
-        """Second kernel, used for A^T by the zero-padded operator (sgp.py:157); numpy [ny,nx] / [n,ny,nx]."""
+        """Second kernel, used for A^T by the zero-padded operator (sgp.py:157); numpy or CUDA tensor, [ny,nx] / [n,ny,nx]."""
+        if _is_tensor(psf):
+            t = psf.contiguous()
+            n = 1 if t.dim() == 2 else t.shape[0]
+            check(lib().bsgp_set_psf_adjoint(self._h, t.data_ptr(), n, _stream_ptr()))
+            self._psf_adj_keepalive = t
+            return n
         a = np.ascontiguousarray(psf, dtype=_NP[self.dtype])
         n = 1 if a.ndim == 2 else a.shape[0]
         if a.shape[-2:] != (self.ny, self.nx):
@@ -191,7 +197,7 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
     betaParam scalar or [B].  Keyword arguments are those of sgp()/sgp_betaDiv() (sgp.py:41-47,
     506-513).  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (asynchronous on the
     current stream).  ``padded=True`` selects the zero-padded operator of use_original_SGP_Afunction=False
-    (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size, numpy inputs only."""
+    (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size."""
     if divergence not in ("kl", "beta"):
         raise ValueError("divergence must be 'kl' or 'beta'")
     if padded:
@@ -247,21 +253,45 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
 
 
 def _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw):
-    """Embed into the padded grid, solve there with the window mask, crop (see PaddedGeometry)."""
-    if _is_tensor(gn):
-        raise NotImplementedError("padded=True takes numpy inputs")
+    """Embed into the padded grid, solve there with the window mask, crop (see PaddedGeometry).  numpy inputs give
+    numpy outputs; CUDA-tensor images stay on the device (the small kernels may be numpy or tensors)."""
+    on_dev = _is_tensor(gn)
+    if on_dev:
+        import torch
+        dtype = {torch.float64: "float64", torch.float32: "float32"}[gn.dtype]
+        device = gn.device.index or 0
     npdt = _NP[dtype]
-    gn = np.asarray(gn, dtype=npdt)
-    psf = np.asarray(psf, dtype=np.float64)
+    if not on_dev:
+        gn = np.asarray(gn, dtype=npdt)
     if gn.ndim != 3:
         raise ValueError("gn must be [batch, ny, nx]")
     B, ny, nx = gn.shape
-    geo = PaddedGeometry(ny, nx, psf.shape[-2], psf.shape[-1])
+    psf_h = psf.detach().cpu().numpy() if _is_tensor(psf) else np.asarray(psf)
+    psf_h = np.asarray(psf_h, dtype=np.float64)
+    geo = PaddedGeometry(ny, nx, psf_h.shape[-2], psf_h.shape[-1])
     if geo.P > 8192:
         raise ValueError(f"padded grid {geo.P} exceeds the largest supported side (8192)")
     plan = get_plan(geo.P, geo.P, dtype, device)
-    big, div_a = geo.kernel(psf, npdt)
-    bigt, div_at = geo.kernel(np.conj(np.swapaxes(psf, -1, -2)), npdt)          # psf.conj().T, sgp.py:157
+    big, div_a = geo.kernel(psf_h, npdt)
+    bigt, div_at = geo.kernel(np.conj(np.swapaxes(psf_h, -1, -2)), npdt)          # psf.conj().T, sgp.py:157
+    extra = dict(region=geo.region, div_a=div_a, div_at=div_at, adjoint_second_psf=True)
+    if on_dev:
+        import torch
+        with torch.cuda.device(gn.device):
+            if plan.set_psf(torch.as_tensor(big, device=gn.device)) not in (1, B) or \
+                    plan.set_psf_adjoint(torch.as_tensor(bigt, device=gn.device)) not in (1, B):
+                raise ValueError("psf must be one kernel or one per batch entry")
+
+            def emb(t):
+                out = torch.zeros(t.shape[:-2] + (geo.P, geo.P), dtype=gn.dtype, device=gn.device)
+                out[..., geo.rows, geo.cols] = t
+                return out
+
+            bkg_p = emb(bkg) if (_is_tensor(bkg) and bkg.dim() == 3) else bkg
+            res = _solve_batch_device(emb(gn), None, bkg_p, divergence, flux, betaParam, None if x0 is None else emb(x0),
+                                      None if obj is None else emb(obj), trace, plan, True, dict(kw, **extra))
+            res.x = res.x[:, geo.rows, geo.cols].contiguous()
+        return res
     if plan.set_psf(big) not in (1, B) or plan.set_psf_adjoint(bigt) not in (1, B):
         raise ValueError("psf must be one kernel or one per batch entry")
     bkg = np.asarray(bkg, dtype=npdt)
@@ -269,8 +299,7 @@ def _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtyp
     res = solve_batch(geo.embed(gn, npdt), None, bkg_p, divergence=divergence, flux=flux, betaParam=betaParam,
                       x0=None if x0 is None else geo.embed(np.asarray(x0, dtype=npdt), npdt),
                       obj=None if obj is None else geo.embed(np.asarray(obj, dtype=npdt), npdt), dtype=dtype, device=device,
-                      trace=trace, plan=plan, psf_is_set=True, region=geo.region, div_a=div_a, div_at=div_at,
-                      adjoint_second_psf=True, **kw)
+                      trace=trace, plan=plan, psf_is_set=True, **extra, **kw)
     res.x = np.ascontiguousarray(res.x[:, geo.rows, geo.cols])
     return res
 

@@ -451,3 +451,19 @@ def test_non_square_images_against_oracle(bs, shape):
     assert int(r.iters[0]) == o.iters
     assert np.abs(r.discr[0, :o.iters + 1] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
     assert np.abs(r.x[0] - o.x).max() <= 1e-8 * np.abs(o.x).max()
+
+
+def test_padded_operator_device_tensors(bs):
+    """CUDA-tensor inputs through the zero-padded operator give the same bits as numpy inputs (odd image size)."""
+    import torch
+    orc, gn, psf = _padded_inputs(bs, 45, 61, 15, 9, nstars=12)
+    gn3 = np.stack([gn, gn[::-1].copy(), gn[:, ::-1].copy()])
+    flux = (gn3 - 300.0).sum(axis=(1, 2))
+    kw = dict(bs.synth.TILE_KWARGS, MAXIT=15)
+    a = bs.sgp_betaDiv_batch(gn3, psf, np.float64(300.0), flux=flux, betaParam=1.0248357, padded=True, **kw)
+    dev = torch.device("cuda:0")
+    t = bs.sgp_betaDiv_batch(torch.as_tensor(gn3, device=dev), psf, torch.tensor(300.0, device=dev, dtype=torch.float64),
+                             flux=torch.as_tensor(flux, device=dev), betaParam=1.0248357, padded=True, **kw)
+    torch.cuda.synchronize()
+    assert t.x.shape == (3, 45, 61)
+    assert np.array_equal(t.x.cpu().numpy(), a.x) and np.array_equal(t.iters.cpu().numpy(), a.iters)
