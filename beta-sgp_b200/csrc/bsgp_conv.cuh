@@ -82,7 +82,7 @@ template <class Ctx> BSGP_DEV void fill_pos_table(Ctx& ctx, const FftPlan& pl, u
 
 // Producer: In fetch(i); V2 eval(i, In) for the slab pixel pair (i, i + 1), i = local_row * nx + col.
 template <int U, class Ctx, typename T, class Fetch, class Eval>
-BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, unsigned ppx_off, cplx<T>* spec, Fetch& fetch, Eval& eval) {
+BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, cplx<T>* spec, Fetch& fetch, Eval& eval) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
     const RowGeom g = row_geom(gg);                          // scalars in registers; the FFT plan stays where it is
@@ -128,7 +128,7 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
             row[fpad(c + 1, ps)] = cmake<T>(v0.y, v1.y);
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
+        fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off, tw_split);
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int p = e >> g.lg_hx, k = e & (g.hx - 1);
             const cplx<T>* a = ws + p * g.rowstride;
@@ -154,7 +154,7 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
 // row 0 = kx 0, rows 1..hx-1 = kx, row hx = kx nx/2.  Not inlined: it does not depend on the
 // producer / consumer, so all convolutions of the solver share one copy of the code.
 template <class Ctx, typename T>
-BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, unsigned twy_off, cplx<T>* spec, cplx<T>* tf, int mode) {
+BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, unsigned twy_off, int tw_split, cplx<T>* spec, cplx<T>* tf, int mode) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     constexpr int U = 8;
     struct { int ny, nx, hx, lg_ny, lg_col_tile, col_tile, colstride, cols_per_cta; } g;      // register copies
@@ -187,7 +187,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
                 ws[(e0 & (ct - 1)) * g.colstride + fpad(e0 >> g.lg_col_tile, ps)] = spec[(size_t)(e0 >> g.lg_col_tile) * g.hx + cc0 + (e0 & (ct - 1))];
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
+        fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy, twy_off, tw_split);
         if (mode == CONV_MAKE_TF) {
             // column FFT of 2*A holds 2*TF; store TF * 0.5/(nx ny)
             const T sc = (T)0.25 / ((T)g.nx * (T)g.ny);
@@ -249,7 +249,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
+        fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off, tw_split);
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int row = e >> g.lg_col_tile, cl = e & (ct - 1);
             spec[(size_t)row * g.hx + cc0 + cl] = ws[cl * g.colstride + fpad(row, ps)];
@@ -260,7 +260,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 
 // Consumer: In fetch(i); void apply(i, In, V2 value) for the slab pixel pair (i, i + 1).
 template <int U, class Ctx, typename T, class Fetch, class Apply>
-BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
+BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
     constexpr int UL = 4;
@@ -303,7 +303,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
+        fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off, tw_split);
         {
             int e0 = ctx.tid;
             for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {

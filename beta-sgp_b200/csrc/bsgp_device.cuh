@@ -221,7 +221,7 @@ struct SmemPlan {
     unsigned off_ppx;       // padded-position table of the row transforms (nx x u16)
     unsigned off_ws;        // FFT workspace
     unsigned off_bufs;      // resident slab buffers
-    int tw_smem;
+    int tw_smem;            // 0: twiddles stay in global memory, 1: full tables in shared memory, 2: two-level tables
 };
 
 }  // namespace bsgp

@@ -101,7 +101,14 @@ template <int LOG2R, bool INV, typename T> BSGP_DEV void dft_r(cplx<T>* v) {
 // (make_fft_plan guarantees this), the R elements of a task sit at a CONSTANT padded stride:
 //   fpad(p0 + r S) = fpad(p0) + r (S + S / 2^ps)      (S >= 2^ps),      fpad(p0 + r) = fpad(p0) + r   (final stage),
 // so one base address per task replaces two shifts and two adds per element.
-template <int LOG2R, bool INV, typename T>
+// SPLIT: tw is a two-level table [W^0 .. W^63][W^0, W^64, W^128, ...] and W^k = tw[64 + (k >> 6)] * tw[k & 63] (long transforms,
+// whose full table does not fit shared memory: one extra complex multiply instead of an L2 round trip per twiddle).
+template <typename T, bool SPLIT> BSGP_DEV cplx<T> twiddle_at(const cplx<T>* tw, int k) {
+    if (SPLIT) return cmul(tw[64 + (k >> 6)], tw[k & 63]);
+    return tw[k];
+}
+
+template <int LOG2R, bool INV, bool SPLIT, typename T>
 BSGP_DEV void stage_task(cplx<T>* a, int spad, bool twiddle, int j, const cplx<T>* tw, int lg_twstep) {
     constexpr int R = 1 << LOG2R;
     cplx<T> v[R];
@@ -111,12 +118,12 @@ BSGP_DEV void stage_task(cplx<T>* a, int spad, bool twiddle, int j, const cplx<T
         dft_r<LOG2R, false>(v);
         if (twiddle) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tw[(q * j) << lg_twstep]);
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], twiddle_at<T, SPLIT>(tw, (q * j) << lg_twstep));
         }
     } else {
         if (twiddle) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], tw[(q * j) << lg_twstep]);
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], twiddle_at<T, SPLIT>(tw, (q * j) << lg_twstep));
         }
         dft_r<LOG2R, true>(v);
     }
@@ -124,7 +131,7 @@ BSGP_DEV void stage_task(cplx<T>* a, int spad, bool twiddle, int j, const cplx<T
     for (int r = 0; r < R; ++r) a[r * spad] = v[r];
 }
 
-template <int LOG2R, bool INV, class Ctx, typename T>
+template <int LOG2R, bool INV, bool SPLIT, class Ctx, typename T>
 BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, int log2n, int ps, int lgL, const cplx<T>* tw) {
     const int lg_per = log2n - LOG2R;             // butterflies per transform
     const int lgS = lgL - LOG2R;
@@ -136,12 +143,12 @@ BSGP_DEV void run_stage(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, int log2n,
         const int f = t >> lg_per, u = t & ((1 << lg_per) - 1);
         const int j = u & (S - 1);
         const int p0 = ((u >> lgS) << lgL) + j;
-        stage_task<LOG2R, INV>(ws + f * fstride + p0 + (p0 >> ps), spad, lgS > 0, j, tw, lg_tw);
+        stage_task<LOG2R, INV, SPLIT>(ws + f * fstride + p0 + (p0 >> ps), spad, lgS > 0, j, tw, lg_tw);
     }
     ctx.sync();
 }
 
-template <bool INV, class Ctx, typename T>
+template <bool INV, bool SPLIT, class Ctx, typename T>
 BSGP_DEV void run_stages(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
     const int log2n = pl.log2n, ps = pl.pad_shift, ns = pl.nstages;
     int lgL = INV ? 0 : log2n;
@@ -149,9 +156,9 @@ BSGP_DEV void run_stages(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const Fft
         const int lg_r = pl.log2r[INV ? ns - 1 - i : i];
         if (INV) lgL += lg_r;
         switch (lg_r) {
-            case 1: run_stage<1, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
-            case 2: run_stage<2, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
-            default: run_stage<3, INV>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+            case 1: run_stage<1, INV, SPLIT>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+            case 2: run_stage<2, INV, SPLIT>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
+            default: run_stage<3, INV, SPLIT>(ctx, ws, nfft, fstride, log2n, ps, lgL, tw); break;
         }
         if (!INV) lgL -= lg_r;
     }
@@ -160,14 +167,17 @@ BSGP_DEV void run_stages(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const Fft
 constexpr unsigned kNoSmem = 0xffffffffu;
 
 // nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout), ws = shared memory at byte
-// offset ws_off; twiddles at shared-memory offset tw_off, or through the generic pointer tw when tw_off == kNoSmem.
+// offset ws_off.
 // Ends with a barrier.
 // Not inlined: the solver runs five convolutions, all sharing one copy of each direction.
+// tw_off: byte offset of the twiddle table in shared memory (kNoSmem: read the full table through the generic pointer tw);
+// tw_split: the shared-memory table is the two-level one.
 template <bool INV, class Ctx, typename T>
-BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off) {
+BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off, int tw_split) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
-    if (tw_off != kNoSmem) run_stages<INV>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));   // twiddles in shared memory
-    else run_stages<INV>(ctx, ws, nfft, fstride, pl, tw);
+    if (tw_off == kNoSmem) run_stages<INV, false>(ctx, ws, nfft, fstride, pl, tw);
+    else if (tw_split) run_stages<INV, true>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
+    else run_stages<INV, false>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
 }
 
 }  // namespace bsgp

@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             };
             auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
             T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
             const T* s0 = src + (size_t)r0 * nx;
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
             auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
-            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, spec, cf, ca);
+            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
             };
             auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, a.spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
             T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
             const T* s0 = src + (size_t)r0 * nx;
@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
             auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
             auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, pf, pe);
+            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
-            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, off_ppx, a.spec, cf, ca);
+            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -248,6 +248,7 @@ static void plan_free_buffers(bsgp_plan* p) {
 }
 
 static inline size_t up128(size_t v) { return (v + 127) & ~(size_t)127; }
+static inline size_t tw_table_entries(int mode, int n) { return mode == 1 ? (size_t)n : (size_t)64 + (size_t)(n >> 6); }
 
 // Residency priority: the two projection buffers (read E times per iteration), then the arrays with
 // the most touches per iteration; the background image last (unused when the background is a scalar).
@@ -279,12 +280,10 @@ template <typename T> static int plan_setup_frame(bsgp_plan* p) {
     size_t off = up128(sizeof(SharedCtl));
     sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
-    sp.tw_smem = tw_bytes <= 16384;
+    sp.tw_smem = tw_bytes <= 16384 ? 1 : 2;             // long transforms: two-level tables (64 + n/64 entries)
     sp.off_twx = sp.off_twy = (unsigned)off;
-    if (sp.tw_smem) {
-        off = up128(off + (size_t)p->nx * sizeof(cplx<T>));
-        if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + (size_t)p->ny * sizeof(cplx<T>)); }
-    }
+    off = up128(off + tw_table_entries(sp.tw_smem, p->nx) * sizeof(cplx<T>));
+    if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + tw_table_entries(sp.tw_smem, p->ny) * sizeof(cplx<T>)); }
     sp.off_ppx = (unsigned)off; off = up128(off + (size_t)p->nx * sizeof(unsigned short));
     sp.off_ws = (unsigned)off; off = up128(off + p->ws_bytes);
     sp.off_bufs = (unsigned)off;
@@ -363,13 +362,11 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     size_t off = up128(sizeof(SharedCtl));
     sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
-    sp.tw_smem = tw_bytes <= 16384;
+    sp.tw_smem = tw_bytes <= 16384 ? 1 : 2;             // long transforms: two-level tables (64 + n/64 entries)
     sp.off_twx = (unsigned)off;
     sp.off_twy = (unsigned)off;
-    if (sp.tw_smem) {
-        off = up128(off + (size_t)p->nx * sizeof(cplx<T>));
-        if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + (size_t)p->ny * sizeof(cplx<T>)); }
-    }
+    off = up128(off + tw_table_entries(sp.tw_smem, p->nx) * sizeof(cplx<T>));
+    if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + tw_table_entries(sp.tw_smem, p->ny) * sizeof(cplx<T>)); }
     sp.off_ppx = (unsigned)off; off = up128(off + (size_t)p->nx * sizeof(unsigned short));
     sp.off_ws = (unsigned)off; off = up128(off + p->ws_bytes);
     sp.off_bufs = (unsigned)off;

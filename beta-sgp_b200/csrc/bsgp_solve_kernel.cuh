@@ -10,6 +10,15 @@
 
 namespace bsgp {
 
+// shared-memory twiddle table: mode 1 = the full table W_n^k, mode 2 = two-level [W^0 .. W^63][W^(64 m)] (bsgp_fft.cuh)
+template <class Ctx, typename T> __device__ __forceinline__ void fill_twiddles(Ctx& ctx, int mode, int n, const cplx<T>* tw, cplx<T>* dst) {
+    if (mode == 1) {
+        for (int k = ctx.tid; k < n; k += ctx.nt) dst[k] = tw[k];
+    } else if (mode == 2) {
+        for (int k = ctx.tid; k < 64 + (n >> 6); k += ctx.nt) dst[k] = (k < 64) ? tw[k] : tw[(k - 64) << 6];
+    }
+}
+
 template <typename T, int NT, int MINB, bool MK>
 __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
     unsigned char* smem = dyn_smem();
@@ -27,10 +36,8 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
     }
     cplx<T>* twx_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twx);
     cplx<T>* twy_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twy);
-    if (sp.tw_smem) {
-        for (int k = ctx.tid; k < a.g.nx; k += ctx.nt) twx_s[k] = a.twx[k];
-        if (sp.off_twy != sp.off_twx) for (int k = ctx.tid; k < a.g.ny; k += ctx.nt) twy_s[k] = a.twy[k];
-    }
+    fill_twiddles(ctx, sp.tw_smem, a.g.nx, a.twx, twx_s);
+    if (sp.off_twy != sp.off_twx) fill_twiddles(ctx, sp.tw_smem, a.g.ny, a.twy, twy_s);
     unsigned short* ppx = reinterpret_cast<unsigned short*>(smem + sp.off_ppx);
     fill_pos_table(ctx, a.g.px, ppx);
     if (ctx.tid == 0) {
@@ -41,6 +48,7 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
         S->twx = a.twx; S->twy = a.twy;
         S->twx_off = sp.tw_smem ? sp.off_twx : kNoSmem;
         S->twy_off = sp.tw_smem ? sp.off_twy : kNoSmem;
+        S->tw_split = sp.tw_smem == 2;
     }
     __syncthreads();
     for (;;) {
@@ -66,10 +74,8 @@ __global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a
     for (int b = 0; b < NBUF; ++b) buf[b] = a.work + (size_t)b * npix + (size_t)ctx.rank * nslab;
     cplx<T>* twx_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twx);
     cplx<T>* twy_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twy);
-    if (sp.tw_smem) {
-        for (int k = ctx.tid; k < a.g.nx; k += ctx.nt) twx_s[k] = a.twx[k];
-        if (sp.off_twy != sp.off_twx) for (int k = ctx.tid; k < a.g.ny; k += ctx.nt) twy_s[k] = a.twy[k];
-    }
+    fill_twiddles(ctx, sp.tw_smem, a.g.nx, a.twx, twx_s);
+    if (sp.off_twy != sp.off_twx) fill_twiddles(ctx, sp.tw_smem, a.g.ny, a.twy, twy_s);
     fill_pos_table(ctx, a.g.px, reinterpret_cast<unsigned short*>(smem + sp.off_ppx));
     if (ctx.tid == 0) {
         S->geom = a.g;
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a
         S->twx = a.twx; S->twy = a.twy;
         S->twx_off = sp.tw_smem ? sp.off_twx : kNoSmem;
         S->twy_off = sp.tw_smem ? sp.off_twy : kNoSmem;
+        S->tw_split = sp.tw_smem == 2;
     }
     __syncthreads();
     for (int img = 0; img < a.batch; ++img) {

@@ -59,6 +59,7 @@ template <typename T> struct ImgState {
     const cplx<T>* twx; const cplx<T>* twy; cplx<T>* spec; cplx<T>* tf;
     unsigned ws_off, ppx_off;        // FFT workspace and position table: byte offsets into dynamic shared memory
     unsigned twx_off, twy_off;       // twiddle tables in shared memory, or kNoSmem (then twx / twy are used)
+    int tw_split;                    // the shared-memory tables are two-level (long transforms)
     ConvGeom geom;
     int nslab, bkg_img, init_recon, has_cap, pflag, want_err, stop2;
     int masked, reg[4];              // zero-padded operator: valid window [reg0, reg1) x [reg2, reg3) of the FFT grid
@@ -321,7 +322,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
     const T* src = which ? S->gn : S->x;
     auto pf = [&](int i) { In1<T> r; r.a = ld2(src, i); return r; };
     auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
@@ -344,7 +345,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, c
         st2(xtf, i, xt);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
@@ -367,7 +368,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx,
         return mk2(inside<MK>(R, i) ? nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))) : (T)0,
                    inside<MK>(R, i + 1) ? nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))) : (T)0);
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer: g = 1 - w (KL) or den^(beta-1) - w                            sgp.py:262 / 705
@@ -381,7 +382,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx
         return (kind == 0) ? nsub((T)1, w) : nsub(p1, w);
     };
     auto ca = [&](int i, const In1<T>& in, V2<T> w) { st2(gr, i, mk2(one(inside<MK>(R, i), in.a.x, w.x), one(inside<MK>(R, i + 1), in.a.y, w.y))); };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
 }
 
 // consumer: bounds of the scaling matrix from y = flux/(flux+bkg) * A^T(gn)     sgp.py:268-270 / 712-714
@@ -399,7 +400,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx,
         if (yv > hi) hi = yv;
     };
     auto ca = [&](int i, const In1<T>& in, V2<T> w) { one(inside<MK>(R, i), in.a.x, w.x); one(inside<MK>(R, i + 1), in.a.y, w.y); };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R2 r; r.a = lo; r.b = hi;
     return r;
 }
@@ -481,7 +482,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx
         st2(dbuf, i, d);
         return d;
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
     return gd;
 }
 
@@ -506,7 +507,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, 
         st2(dtf, i, dt);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
@@ -593,7 +594,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, con
         gnew.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
         st2(gr, i, gnew);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R7 r;
 #pragma unroll
     for (int k = 0; k < 7; ++k) r.v[k] = bb[k];
@@ -612,7 +613,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_store_out(Ctx ctx, const 
 // the two column passes between a producer and a consumer
 template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgState<T>* S, cplx<T>* tf, int mode) {
     ctx.cluster_sync();
-    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->twy_off, S->spec, tf, mode);
+    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->twy_off, S->tw_split, S->spec, tf, mode);
     ctx.cluster_sync();
 }
 

@@ -58,8 +58,8 @@ template <typename T> struct HostPlan {
                     In1<T> q; q.a = ld2(psf + (size_t)((r0 + row + ny / 2) & (ny - 1)) * nx, (c + nx / 2) & (nx - 1)); return q;
                 };
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), pf, pe);
-                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), out.data(), CONV_MAKE_TF);
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
+                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), out.data(), CONV_MAKE_TF);
             }
     }
     void apply(const T* x, T* y, int adjoint) {
@@ -73,9 +73,9 @@ template <typename T> struct HostPlan {
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
                 auto cf = [&](int) { In1<T> q; q.a = mk2((T)0, (T)0); return q; };
                 auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(y + off, i, v); };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), pf, pe);
-                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
-                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), kNoSmem, ppx_off, spec.data(), cf, ca);
+                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
+                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
+                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), cf, ca);
             }
     }
 };
@@ -83,19 +83,24 @@ template <typename T> struct HostPlan {
 extern "C" {
 
 // 1-D transform check: forward then (optionally) inverse of `nfft` rows of length n (complex interleaved)
-int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after) {
+int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after, int split_twiddles) {
     FftPlan pl;
     if (!make_fft_plan(n, &pl)) return 1;
     std::vector<cplx<double>> tw;
     make_twiddles<double>(n, tw);
     const int stride = pl.plen + 1;
-    std::vector<cplx<double>> ws((size_t)nfft * stride);
+    // emulated shared memory: [workspace][two-level twiddle table]
+    const size_t ws_elems = (size_t)nfft * stride, tab_elems = 64 + (size_t)(n >> 6);
+    std::vector<cplx<double>> arena(ws_elems + tab_elems);
+    cplx<double>* ws = arena.data();
+    for (size_t k = 0; k < tab_elems; ++k) arena[ws_elems + k] = (k < 64) ? tw[k % n] : tw[((k - 64) << 6) % n];
     for (int f = 0; f < nfft; ++f)
         for (int i = 0; i < n; ++i) ws[(size_t)f * stride + fpad(i, pl.pad_shift)] = cmake<double>(in[2 * ((size_t)f * n + i)], in[2 * ((size_t)f * n + i) + 1]);
     HostCtx ctx;
-    g_emul_smem = reinterpret_cast<unsigned char*>(ws.data());
-    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), kNoSmem);
-    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), kNoSmem);
+    g_emul_smem = reinterpret_cast<unsigned char*>(arena.data());
+    const unsigned tw_off = split_twiddles ? (unsigned)(ws_elems * sizeof(cplx<double>)) : kNoSmem;
+    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off, split_twiddles);
+    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off, split_twiddles);
     for (int f = 0; f < nfft; ++f)
         for (int k = 0; k < n; ++k) {
             const int p = inverse_after ? k : pos_of_freq(pl, k);
@@ -149,7 +154,7 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     HostCtx ctx;
     ImgState<double> S;
     memset(&S, 0, sizeof(S));
-    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem;
+    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem; S.tw_split = 0;
     pl.bind();
     if (params->region[1] > params->region[0]) solve_image<double, true>(ctx, a, &S, buf, pl.tf.data(), psf_adj ? pl.tf_adj.data() : pl.tf.data(), 0);
     else solve_image<double, false>(ctx, a, &S, buf, pl.tf.data(), psf_adj ? pl.tf_adj.data() : pl.tf.data(), 0);

@@ -63,12 +63,13 @@ def test_emulated_fft_stages(n):
     rng = np.random.default_rng(n)
     x = rng.normal(size=(3, n)) + 1j * rng.normal(size=(3, n))
     xin = np.ascontiguousarray(x).view(np.float64).copy()
-    for inverse_after in (0, 1):
-        out = np.zeros_like(xin)
-        assert L.emul_fft1d(n, 3, xin.ctypes.data_as(P), out.ctypes.data_as(P), inverse_after) == 0
-        got = out.view(np.complex128).reshape(3, n)
-        ref = np.fft.fft(x, axis=1) if not inverse_after else x * n
-        assert np.abs(got - ref).max() <= 2e-15 * np.abs(ref).max() * np.log2(n)
+    for split in ((0, 1) if n >= 64 else (0,)):          # full twiddle table / two-level table (long transforms)
+        for inverse_after in (0, 1):
+            out = np.zeros_like(xin)
+            assert L.emul_fft1d(n, 3, xin.ctypes.data_as(P), out.ctypes.data_as(P), inverse_after, split) == 0
+            got = out.view(np.complex128).reshape(3, n)
+            ref = np.fft.fft(x, axis=1) if not inverse_after else x * n
+            assert np.abs(got - ref).max() <= 2e-15 * np.abs(ref).max() * np.log2(n)
 
 
 @pytest.mark.parametrize("ny,nx,G,ws", [(32, 32, 1, 1 << 20), (32, 32, 2, 1 << 20), (64, 64, 4, 1 << 20), (256, 256, 8, 72 * 1024),
