@@ -99,8 +99,9 @@ def lib():
     L.bsgp_plan_configure.argtypes = [vp, ip, ip]
     L.bsgp_set_psf.argtypes = [vp, vp, ip, vp]
     L.bsgp_set_psf_host.argtypes = [vp, vp, ip]
-    L.bsgp_set_psf_adjoint.argtypes = [vp, vp, ip, vp]
-    L.bsgp_set_psf_adjoint_host.argtypes = [vp, vp, ip]
+    if hasattr(L, "bsgp_set_psf_adjoint"):            # absent only in older builds loaded through BSGP_LIB for A/B runs
+        L.bsgp_set_psf_adjoint.argtypes = [vp, vp, ip, vp]
+        L.bsgp_set_psf_adjoint_host.argtypes = [vp, vp, ip]
     L.bsgp_solve_batch.argtypes = [vp, C.POINTER(Params), ip, C.POINTER(Inputs), C.POINTER(Outputs), vp]
     L.bsgp_solve_batch_host.argtypes = [vp, C.POINTER(Params), ip, C.POINTER(Inputs), C.POINTER(Outputs)]
     L.bsgp_apply_psf.argtypes = [vp, vp, vp, ip, ip, vp]

@@ -9,7 +9,7 @@
 //                  part) and untangled into two half spectra.  Values come from a producer functor
 //                  (so the elementwise step that creates the input is fused in) and the half
 //                  spectra go to the cluster's exchange buffer in global memory
-//                  spec[ny][hx], hx = nx/2; column 0 packs the two real columns kx = 0 and
+//                  spec (ny x hx, hx = nx/2, stored in column panels, see spec_idx); column 0 packs the two real columns kx = 0 and
 //                  kx = nx/2 as (re, im).
 //   cols         : CTA `rank` owns packed spectrum columns [rank*hx/G, (rank+1)*hx/G): forward
 //                  column FFT, multiply by the precomputed PSF spectrum (or its conjugate),
@@ -42,6 +42,7 @@ struct ConvGeom {
     int row_tile_pairs;      // row pairs per workspace tile (divides rows_per_cta / 2), power of two
     int col_tile;            // columns per workspace tile (divides cols_per_cta), power of two
     int lg_col_tile;
+    int lg_cp;               // log2 of the panel width of the exchange buffer: cols_per_cta (narrow column tiles) or hx (row-major)
     int rowstride;           // padded complex elements per row pair in the workspace
     int colstride;           // padded complex elements per column in the workspace (odd)
     FftPlan px, py;
@@ -51,12 +52,25 @@ enum ConvMode { CONV_TF = 0, CONV_CTF = 1, CONV_MAKE_TF = 2 };
 
 // the scalars of ConvGeom the row passes need, copied to registers once per pass (the geometry itself
 // lives in shared memory, where every store through another pointer would force a reload)
-struct RowGeom { int nx, hx, lg_nx, lg_hx, rows_per_cta, row_tile_pairs, rowstride, ps; };
+struct RowGeom { int nx, hx, lg_nx, lg_hx, lg_ny, lg_cp, rows_per_cta, row_tile_pairs, rowstride, ps; };
 BSGP_DEV RowGeom row_geom(const ConvGeom& g) {
     RowGeom r;
-    r.nx = g.nx; r.hx = g.hx; r.lg_nx = g.lg_nx; r.lg_hx = g.lg_hx; r.rows_per_cta = g.rows_per_cta;
+    r.nx = g.nx; r.hx = g.hx; r.lg_nx = g.lg_nx; r.lg_hx = g.lg_hx; r.lg_ny = g.lg_ny; r.lg_cp = g.lg_cp; r.rows_per_cta = g.rows_per_cta;
     r.row_tile_pairs = g.row_tile_pairs; r.rowstride = g.rowstride; r.ps = g.px.pad_shift;
     return r;
+}
+
+// Exchange-buffer layout in frame mode: column panels.  Element (row, k) of the half spectrum lives at
+//   ((k >> lg_cp) * ny + row) << lg_cp | (k & (cp - 1)),          cp = 2^lg_cp = cols_per_cta,
+// i.e. the cp columns one CTA transforms form one contiguous [ny][cp] panel.  The row passes write / read cp-element
+// chunks (>= 256 bytes), and the column pass of a CTA walks its own panel only: a column tile narrower than the
+// panel (long columns leave room for a single one in the workspace) still touches every 32-byte sector of the panel
+// exactly once per two columns, with the neighbouring column served by L2, instead of one sector per 64 KB row.
+// PANEL is a compile-time property of the execution context (Ctx::kFrame): the cluster kernels keep the plain
+// row-major buffer (their column tiles are >= 8 columns wide, and they are sensitive to every extra register).
+template <bool PANEL> BSGP_DEV size_t spec_idx(int row, int k, int lg_ny, int lg_cp, int hx) {
+    if (!PANEL) return (size_t)row * hx + k;
+    return ((((size_t)(k >> lg_cp) << lg_ny) + (size_t)row) << lg_cp) | (size_t)(k & ((1 << lg_cp) - 1));
 }
 
 // two adjacent pixels
@@ -128,7 +142,8 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
             row[fpad(c + 1, ps)] = cmake<T>(v0.y, v1.y);
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off, tw_split);
+        if (Ctx::kFrame && tw_split) fft_batch_split<false, Ctx, T>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx_off);
+        else fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int p = e >> g.lg_hx, k = e & (g.hx - 1);
             const cplx<T>* a = ws + p * g.rowstride;
@@ -143,8 +158,8 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 B = cmake<T>(zk.im + zm.im, zm.re - zk.re);
             }
             const size_t row = (size_t)(r0 + 2 * (pair0 + p));
-            spec[row * g.hx + k] = A;
-            spec[(row + 1) * g.hx + k] = B;
+            spec[spec_idx<Ctx::kFrame>((int)row, k, g.lg_ny, g.lg_cp, g.hx)] = A;
+            spec[spec_idx<Ctx::kFrame>((int)row + 1, k, g.lg_ny, g.lg_cp, g.hx)] = B;
         }
         ctx.sync();
     }
@@ -157,8 +172,8 @@ template <class Ctx, typename T>
 BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, unsigned twy_off, int tw_split, cplx<T>* spec, cplx<T>* tf, int mode) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     constexpr int U = 8;
-    struct { int ny, nx, hx, lg_ny, lg_col_tile, col_tile, colstride, cols_per_cta; } g;      // register copies
-    g.ny = gp->ny; g.nx = gp->nx; g.hx = gp->hx; g.lg_ny = gp->lg_ny; g.lg_col_tile = gp->lg_col_tile; g.col_tile = gp->col_tile;
+    struct { int ny, nx, hx, lg_ny, lg_col_tile, col_tile, colstride, cols_per_cta, lg_cp; } g;      // register copies
+    g.ny = gp->ny; g.nx = gp->nx; g.hx = gp->hx; g.lg_ny = gp->lg_ny; g.lg_col_tile = gp->lg_col_tile; g.col_tile = gp->col_tile; g.lg_cp = gp->lg_cp;
     g.colstride = gp->colstride; g.cols_per_cta = gp->cols_per_cta;
     const FftPlan& py = gp->py;
     const int c0 = ctx.rank * g.cols_per_cta;
@@ -175,7 +190,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int e = e0 + u * ctx.nt;
-                    v[u] = spec[(size_t)(e >> g.lg_col_tile) * g.hx + cc0 + (e & (ct - 1))];
+                    v[u] = spec[spec_idx<Ctx::kFrame>(e >> g.lg_col_tile, cc0 + (e & (ct - 1)), g.lg_ny, g.lg_cp, g.hx)];
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -184,10 +199,11 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
                 }
             }
             for (; e0 < total; e0 += ctx.nt)
-                ws[(e0 & (ct - 1)) * g.colstride + fpad(e0 >> g.lg_col_tile, ps)] = spec[(size_t)(e0 >> g.lg_col_tile) * g.hx + cc0 + (e0 & (ct - 1))];
+                ws[(e0 & (ct - 1)) * g.colstride + fpad(e0 >> g.lg_col_tile, ps)] = spec[spec_idx<Ctx::kFrame>(e0 >> g.lg_col_tile, cc0 + (e0 & (ct - 1)), g.lg_ny, g.lg_cp, g.hx)];
         }
         ctx.sync();
-        fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy, twy_off, tw_split);
+        if (Ctx::kFrame && tw_split) fft_batch_split<false, Ctx, T>(ctx, ws_off, ct, g.colstride, py, twy_off);
+        else fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
         if (mode == CONV_MAKE_TF) {
             // column FFT of 2*A holds 2*TF; store TF * 0.5/(nx ny)
             const T sc = (T)0.25 / ((T)g.nx * (T)g.ny);
@@ -249,10 +265,11 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off, tw_split);
+        if (Ctx::kFrame && tw_split) fft_batch_split<true, Ctx, T>(ctx, ws_off, ct, g.colstride, py, twy_off);
+        else fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int row = e >> g.lg_col_tile, cl = e & (ct - 1);
-            spec[(size_t)row * g.hx + cc0 + cl] = ws[cl * g.colstride + fpad(row, ps)];
+            spec[spec_idx<Ctx::kFrame>(row, cc0 + cl, g.lg_ny, g.lg_cp, g.hx)] = ws[cl * g.colstride + fpad(row, ps)];
         }
         ctx.sync();
     }
@@ -291,19 +308,20 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 for (int u = 0; u < UL; ++u) {
                     const int e = e0 + u * ctx.nt;
                     const size_t row = (size_t)(r0 + 2 * (pair0 + (e >> g.lg_hx)));
-                    A[u] = spec[row * g.hx + (e & (g.hx - 1))];
-                    B[u] = spec[(row + 1) * g.hx + (e & (g.hx - 1))];
+                    A[u] = spec[spec_idx<Ctx::kFrame>((int)row, e & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)];
+                    B[u] = spec[spec_idx<Ctx::kFrame>((int)row + 1, e & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)];
                 }
 #pragma unroll
                 for (int u = 0; u < UL; ++u) tangle(e0 + u * ctx.nt, A[u], B[u]);
             }
             for (; e0 < total; e0 += ctx.nt) {
                 const size_t row = (size_t)(r0 + 2 * (pair0 + (e0 >> g.lg_hx)));
-                tangle(e0, spec[row * g.hx + (e0 & (g.hx - 1))], spec[(row + 1) * g.hx + (e0 & (g.hx - 1))]);
+                tangle(e0, spec[spec_idx<Ctx::kFrame>((int)row, e0 & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)], spec[spec_idx<Ctx::kFrame>((int)row + 1, e0 & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)]);
             }
         }
         ctx.sync();
-        fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off, tw_split);
+        if (Ctx::kFrame && tw_split) fft_batch_split<true, Ctx, T>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx_off);
+        else fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
         {
             int e0 = ctx.tid;
             for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {

@@ -42,6 +42,7 @@ __device__ __forceinline__ unsigned map_to_rank(unsigned addr, int rank) {
 }
 
 struct DeviceCtx {
+    static constexpr bool kFrame = false;     // cluster mode: row-major exchange buffer, full twiddle tables
     int tid, nt, rank, G;
     SharedCtl* sh;
     int parity;        // bit 0: inbox half in use; bits 1, 2: phase of mbar[0], mbar[1]
@@ -144,6 +145,7 @@ __device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
 // per lane in rank order, then a fixed shuffle tree), so all controllers agree bit for bit.
 // -------------------------------------------------------------------------------------------------
 struct GridCtx {
+    static constexpr bool kFrame = true;      // frame mode: panel exchange buffer, two-level twiddle tables allowed
     int tid, nt, rank, G;
     SharedCtl* sh;
     double* gpart;      // [2][G][kMaxK]

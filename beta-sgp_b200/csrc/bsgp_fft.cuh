@@ -170,14 +170,19 @@ constexpr unsigned kNoSmem = 0xffffffffu;
 // offset ws_off.
 // Ends with a barrier.
 // Not inlined: the solver runs five convolutions, all sharing one copy of each direction.
-// tw_off: byte offset of the twiddle table in shared memory (kNoSmem: read the full table through the generic pointer tw);
-// tw_split: the shared-memory table is the two-level one.
+// tw_off: byte offset of the full twiddle table in shared memory (kNoSmem: read it through the generic pointer tw).
 template <bool INV, class Ctx, typename T>
-BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off, int tw_split) {
+BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
-    if (tw_off == kNoSmem) run_stages<INV, false>(ctx, ws, nfft, fstride, pl, tw);
-    else if (tw_split) run_stages<INV, true>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
-    else run_stages<INV, false>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
+    if (tw_off != kNoSmem) run_stages<INV, false>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
+    else run_stages<INV, false>(ctx, ws, nfft, fstride, pl, tw);
+}
+
+// The same with the two-level twiddle table at tw_off (long transforms).  A separate function so that the common
+// case above keeps its code size: the small-image kernels are instruction-fetch bound.
+template <bool INV, class Ctx, typename T>
+BSGP_NOINLINE void fft_batch_split(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, unsigned tw_off) {
+    run_stages<INV, true>(ctx, smem_at<cplx<T>>(ws_off), nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
 }
 
 }  // namespace bsgp

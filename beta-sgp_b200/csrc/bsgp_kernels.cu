@@ -248,7 +248,7 @@ static void plan_free_buffers(bsgp_plan* p) {
 }
 
 static inline size_t up128(size_t v) { return (v + 127) & ~(size_t)127; }
-static inline size_t tw_table_entries(int mode, int n) { return mode == 1 ? (size_t)n : (size_t)64 + (size_t)(n >> 6); }
+static inline size_t tw_table_entries(int mode, int n) { return mode == 0 ? 0 : (mode == 1 ? (size_t)n : (size_t)64 + (size_t)(n >> 6)); }
 
 // Residency priority: the two projection buffers (read E times per iteration), then the arrays with
 // the most touches per iteration; the background image last (unused when the background is a scalar).
@@ -362,7 +362,7 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     size_t off = up128(sizeof(SharedCtl));
     sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
-    sp.tw_smem = tw_bytes <= 16384 ? 1 : 2;             // long transforms: two-level tables (64 + n/64 entries)
+    sp.tw_smem = tw_bytes <= 16384 ? 1 : 0;             // cluster mode: full tables in shared memory, or global
     sp.off_twx = (unsigned)off;
     sp.off_twy = (unsigned)off;
     off = up128(off + tw_table_entries(sp.tw_smem, p->nx) * sizeof(cplx<T>));

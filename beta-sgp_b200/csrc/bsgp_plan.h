@@ -87,6 +87,7 @@ inline bool make_geom(int ny, int nx, int G, size_t elem_bytes /* sizeof(cplx<T>
     g->row_tile_pairs = rtp;
     g->col_tile = ct;
     g->lg_col_tile = ilog2(ct);
+    g->lg_cp = ilog2(g->cols_per_cta);              // panel width of the exchange buffer in frame mode (bsgp_conv.cuh)
     const size_t a = (size_t)rtp * g->rowstride * elem_bytes, b = (size_t)ct * g->colstride * elem_bytes;
     *ws_bytes = a > b ? a : b;
     return true;

@@ -16,6 +16,7 @@
 using namespace bsgp;
 
 struct HostCtx {
+    static constexpr bool kFrame = false;
     int tid = 0, nt = 1, rank = 0, G = 1;
     void sync() {}
     void cluster_sync() {}
@@ -25,7 +26,11 @@ struct HostCtx {
     double now() { return 0.0; }
 };
 
-template <typename T> struct HostPlan {
+struct HostCtxFrame : HostCtx {
+    static constexpr bool kFrame = true;      // panel exchange-buffer layout (frame mode)
+};
+
+template <typename T, class C = HostCtx> struct HostPlan {
     ConvGeom g;
     size_t ws_bytes;
     std::vector<cplx<T>> twx, twy, spec, tf, tf_adj;
@@ -51,7 +56,7 @@ template <typename T> struct HostPlan {
         out.assign((size_t)(g.hx + 1) * ny, cmake<T>(0, 0));
         for (int phase = 0; phase < 2; ++phase)
             for (int r = 0; r < g.G; ++r) {
-                HostCtx ctx; ctx.rank = r; ctx.G = g.G;
+                C ctx; ctx.rank = r; ctx.G = g.G;
                 const int r0 = r * g.rows_per_cta;
                 auto pf = [&](int i) {
                     const int row = i / nx, c = i % nx;
@@ -66,7 +71,7 @@ template <typename T> struct HostPlan {
         const int nx = g.nx;
         for (int phase = 0; phase < 3; ++phase)
             for (int r = 0; r < g.G; ++r) {
-                HostCtx ctx; ctx.rank = r; ctx.G = g.G;
+                C ctx; ctx.rank = r; ctx.G = g.G;
                 const int r0 = r * g.rows_per_cta;
                 const size_t off = (size_t)r0 * nx;
                 auto pf = [&](int i) { In1<T> q; q.a = ld2(x + off, i); return q; };
@@ -99,8 +104,13 @@ int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after
     HostCtx ctx;
     g_emul_smem = reinterpret_cast<unsigned char*>(arena.data());
     const unsigned tw_off = split_twiddles ? (unsigned)(ws_elems * sizeof(cplx<double>)) : kNoSmem;
-    fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off, split_twiddles);
-    if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off, split_twiddles);
+    if (split_twiddles) {
+        fft_batch_split<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw_off);
+        if (inverse_after) fft_batch_split<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw_off);
+    } else {
+        fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
+        if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
+    }
     for (int f = 0; f < nfft; ++f)
         for (int k = 0; k < n; ++k) {
             const int p = inverse_after ? k : pos_of_freq(pl, k);
@@ -114,6 +124,15 @@ int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after
 // circular PSF convolution of one image with the cluster partition emulated rank by rank
 int emul_conv(int ny, int nx, int G, long long ws_limit, const double* x, const double* psf, int adjoint, double* y) {
     HostPlan<double> pl;
+    if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
+    pl.make_tf(psf);
+    pl.apply(x, y, adjoint);
+    return 0;
+}
+
+// the same with the frame-mode (column panel) layout of the exchange buffer
+int emul_conv_frame(int ny, int nx, int G, long long ws_limit, const double* x, const double* psf, int adjoint, double* y) {
+    HostPlan<double, HostCtxFrame> pl;
     if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
     pl.make_tf(psf);
     pl.apply(x, y, adjoint);

@@ -83,12 +83,14 @@ def test_emulated_cluster_convolution(ny, nx, G, ws):
     x = rng.normal(size=(ny, nx))
     psf = rng.random((ny, nx))
     psf /= psf.sum()
-    for adjoint in (0, 1):
-        y = np.zeros((ny, nx))
-        assert L.emul_conv(ny, nx, G, ws, x.ctypes.data_as(P), psf.ctypes.data_as(P), adjoint, y.ctypes.data_as(P)) == 0
-        tf = np.fft.fftn(np.fft.fftshift(psf))
-        ref = np.real(np.fft.ifftn((np.conj(tf) if adjoint else tf) * np.fft.fftn(x)))
-        assert np.abs(y - ref).max() <= 5e-15 * np.abs(ref).max()
+    L.emul_conv_frame.argtypes = L.emul_conv.argtypes
+    for fn in (L.emul_conv, L.emul_conv_frame):            # row-major exchange buffer / column panels (frame mode)
+        for adjoint in (0, 1):
+            y = np.zeros((ny, nx))
+            assert fn(ny, nx, G, ws, x.ctypes.data_as(P), psf.ctypes.data_as(P), adjoint, y.ctypes.data_as(P)) == 0
+            tf = np.fft.fftn(np.fft.fftshift(psf))
+            ref = np.real(np.fft.ifftn((np.conj(tf) if adjoint else tf) * np.fft.fftn(x)))
+            assert np.abs(y - ref).max() <= 5e-15 * np.abs(ref).max()
 
 
 def test_emulated_projection_known_answers(golden):
