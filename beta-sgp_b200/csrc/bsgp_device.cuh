@@ -16,7 +16,7 @@ namespace bsgp {
 
 namespace cg = cooperative_groups;
 
-constexpr int kMaxWarps = 32;
+constexpr int kMaxWarps = 16;      // 512 threads per CTA at most
 constexpr int kMaxG = 16;
 constexpr int kMaxK = 8;
 
@@ -213,6 +213,20 @@ __device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue) {
     const int img = ctx.sh->next_img;
     ctx.cluster_sync();          // nobody may still be reading when the leader claims the next one
     return img;
+}
+
+// Pipelined ingest (bsgp_solve_batch_pinned): the copy engine writes an image into the staging buffer and then its
+// flag; the CTA polls the flag with a system-scope acquire load before its first read of the image.
+__device__ __forceinline__ void wait_ready(const int* flag) {
+    if (threadIdx.x == 0) {
+        int v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v) break;
+            __nanosleep(400);
+        }
+    }
+    __syncthreads();
 }
 
 // dynamic shared memory layout of the persistent kernels (byte offsets, computed by the host)

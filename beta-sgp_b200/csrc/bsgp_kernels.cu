@@ -237,9 +237,23 @@ struct bsgp_plan {
     bool frame = false;          // one image over the whole grid (cooperative launch) instead of one per cluster
     double* gpart = nullptr;     // frame mode: all-reduce partials [2][G][kMaxK]
     size_t workspace_bytes = 0;
+    // pipelined host path (bsgp_solve_batch_pinned): grow-only device staging, ready flags, two private streams
+    void* stage = nullptr; size_t stage_cap = 0;
+    int* ready = nullptr; int* ones_host = nullptr; int ready_cap = 0;
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_flags = nullptr, ev_copy = nullptr, ev_run = nullptr;
 };
 
 template <typename T> static const void* conv_kernel_ptr() { return (const void*)bsgp_conv_kernel<T>; }
+
+static void plan_free_pipeline(bsgp_plan* p) {
+    cudaFree(p->stage); cudaFree(p->ready); cudaFreeHost(p->ones_host);
+    p->stage = nullptr; p->stage_cap = 0; p->ready = nullptr; p->ones_host = nullptr; p->ready_cap = 0;
+    if (p->s_copy) cudaStreamDestroy(p->s_copy);
+    if (p->s_run) cudaStreamDestroy(p->s_run);
+    p->s_copy = p->s_run = nullptr;
+    for (cudaEvent_t* e : {&p->ev_fork, &p->ev_flags, &p->ev_copy, &p->ev_run}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+}
 
 static void plan_free_buffers(bsgp_plan* p) {
     cudaFree(p->twx); cudaFree(p->twy); cudaFree(p->tf); cudaFree(p->tf_adj); cudaFree(p->work); cudaFree(p->spec); cudaFree(p->queue); cudaFree(p->gpart);
@@ -471,7 +485,7 @@ template <typename T> static int apply_psf_t(bsgp_plan* p, const void* x, void* 
 }
 
 template <typename T>
-static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, cudaStream_t st) {
+static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, cudaStream_t st, const int* ready) {
     SolveArgs<T> a;
     memset(&a, 0, sizeof a);
     a.p = *prm; a.g = p->g; a.batch = batch;
@@ -486,6 +500,7 @@ static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_i
     a.ls_trials = out->ls_trials; a.scalars = out->scalars; a.tr_alpha = out->trace_alpha; a.tr_lambda = out->trace_lambda;
     a.tr_beta = out->trace_beta; a.tr_trials = out->trace_trials; a.tr_evals = out->trace_evals;
     a.queue = p->queue;
+    a.ready = p->frame ? nullptr : ready;
     if (p->frame) {
         LaunchCfg fc{p->g.G, 512, 1, p->smem_bytes, st, 1};
         const bool mk = prm->region[1] > prm->region[0];
@@ -563,6 +578,7 @@ int bsgp_plan_destroy(bsgp_plan* p) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     plan_free_buffers(p);
+    plan_free_pipeline(p);
     delete p;
     return BSGP_OK;
 }
@@ -618,7 +634,8 @@ int bsgp_set_psf_adjoint_host(bsgp_plan* p, const void* psf_host, int n_psf) {
     return rc;
 }
 
-int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream) {
+// argument checks + launch; `ready` (device, [batch]) makes the kernel wait for queue item i until ready[i] != 0
+static int solve_checked(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream, const int* ready) {
     if (!p || !prm || !in || !out) return fail(BSGP_E_ARG, "NULL argument");
     if (batch < 1) return fail(BSGP_E_ARG, "batch must be >= 1");
     int rc = check_params(prm);
@@ -640,8 +657,12 @@ int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp
     if (misaligned(in->gn) || misaligned(out->x) || misaligned(in->x0) || misaligned(in->obj) || (in->bkg_is_image && misaligned(in->bkg)))
         return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? solve_t<double>(p, prm, batch, in, out, (cudaStream_t)stream)
-                                : solve_t<float>(p, prm, batch, in, out, (cudaStream_t)stream);
+    return p->dtype == BSGP_F64 ? solve_t<double>(p, prm, batch, in, out, (cudaStream_t)stream, ready)
+                                : solve_t<float>(p, prm, batch, in, out, (cudaStream_t)stream, ready);
+}
+
+int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream) {
+    return solve_checked(p, prm, batch, in, out, stream, nullptr);
 }
 
 // host staging helpers -----------------------------------------------------------------------
@@ -697,6 +718,160 @@ int bsgp_solve_batch_host(bsgp_plan* p, const bsgp_params* prm, int batch, const
     TRY(lt.down(out->ls_trials, B * 4)); TRY(sc.down(out->scalars, B * BSGP_NSCALARS * 8)); TRY(ta.down(out->trace_alpha, B * tr * 8));
     TRY(tl.down(out->trace_lambda, B * tr * 8)); TRY(tb.down(out->trace_beta, B * tr * 8)); TRY(tt.down(out->trace_trials, B * tr * 4));
     TRY(te.down(out->trace_evals, B * tr * 4));
+    return BSGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined host path.  Page-locked image buffers in, page-locked restored images out:
+//   * copy stream : the images go up one queue item at a time, in the order the persistent kernel hands them out,
+//                   each group followed by a 4-byte-per-item copy that raises the items' ready flags;
+//   * run stream  : the solve kernel starts right away and waits per queue item for its flag (wait_ready), so the
+//                   upload of image i+1.. overlaps the restoration of image ..i;
+//   * results     : the kernel stores every restored image straight into the page-locked output (mapped, zero-copy:
+//                   posted writes over PCIe while other images are still being solved); the small per-image outputs
+//                   come back with ordinary copies after the kernel.
+// Small images (< 64 KB) with a permuted queue would need one tiny copy per image; they are uploaded as whole arrays
+// instead (one flag write for everything), still with the zero-copy output.  Frame mode: upload, then launch.
+// ---------------------------------------------------------------------------------------------
+static bool page_locked(const void* h) {
+    if (!h) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream) {
+    if (!p || !prm || !in || !out) return fail(BSGP_E_ARG, "NULL argument");
+    if (batch < 1) return fail(BSGP_E_ARG, "batch must be >= 1");
+    if (!in->gn || !in->bkg || !out->x || !out->iters || !out->status || !out->discr || !out->times) return fail(BSGP_E_ARG, "required pointer is NULL");
+    CU(cudaSetDevice(p->device));
+    if (!page_locked(in->gn) || !page_locked(out->x) || !page_locked(in->x0) || !page_locked(in->obj) || (in->bkg_is_image && !page_locked(in->bkg)))
+        return fail(BSGP_E_ARG, "bsgp_solve_batch_pinned needs page-locked image buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
+    if (in->order) for (int i = 0; i < batch; ++i) if (in->order[i] < 0 || in->order[i] >= batch) return fail(BSGP_E_ARG, "inputs.order is not a permutation of 0..batch-1");
+    int pin_mode = 0;                                             // experiments: 1 = stage x on the device and copy it back at the end, 2 = upload everything before the flags
+    if (const char* e = getenv("BSGP_PIN_MODE")) pin_mode = atoi(e);
+    void* x_mapped = nullptr;
+    CU(cudaHostGetDevicePointer(&x_mapped, out->x, 0));
+    const size_t img = (size_t)p->ny * p->nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
+    // ---- carve the staging arena
+    size_t off = 0;
+    auto carve = [&](bool want, size_t bytes) -> size_t { if (!want) return (size_t)-1; const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_gn = carve(true, B * img), o_bkg = carve(true, in->bkg_is_image ? B * img : B * p->elem);
+    const size_t o_x0 = carve(in->x0 != nullptr, B * img), o_obj = carve(in->obj != nullptr, B * img);
+    const size_t o_flux = carve(in->flux != nullptr, B * 8), o_b0 = carve(in->beta0 != nullptr, B * 8), o_ord = carve(in->order != nullptr, B * 4);
+    const size_t o_xs = carve((pin_mode & 1) != 0, B * img);
+    const size_t o_small = off;                                   // everything from here on is zero-filled output
+    const size_t o_it = carve(true, B * 4), o_st = carve(true, B * 4), o_di = carve(true, B * tr * 8), o_ti = carve(true, B * tr * 8);
+    const size_t o_sv = carve(out->stop_value != nullptr, B * tr * 8), o_er = carve(out->err != nullptr, B * (tr + 1) * 8);
+    const size_t o_bf = carve(out->beta_final != nullptr, B * 8), o_pe = carve(out->proj_evals != nullptr, B * 4), o_lt = carve(out->ls_trials != nullptr, B * 4);
+    const size_t o_sc = carve(out->scalars != nullptr, B * BSGP_NSCALARS * 8);
+    const size_t o_ta = carve(out->trace_alpha != nullptr, B * tr * 8), o_tl = carve(out->trace_lambda != nullptr, B * tr * 8), o_tb = carve(out->trace_beta != nullptr, B * tr * 8);
+    const size_t o_tt = carve(out->trace_trials != nullptr, B * tr * 4), o_te = carve(out->trace_evals != nullptr, B * tr * 4);
+    if (off > p->stage_cap) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(p->stage); p->stage = nullptr; p->stage_cap = 0;
+        CU(cudaMalloc(&p->stage, off));
+        p->stage_cap = off;
+    }
+    if (batch > p->ready_cap) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(p->ready); cudaFreeHost(p->ones_host); p->ready = nullptr; p->ones_host = nullptr; p->ready_cap = 0;
+        CU(cudaMalloc((void**)&p->ready, B * sizeof(int)));
+        CU(cudaHostAlloc((void**)&p->ones_host, B * sizeof(int), cudaHostAllocDefault));
+        for (int i = 0; i < batch; ++i) p->ones_host[i] = 1;
+        p->ready_cap = batch;
+    }
+    if (!p->s_copy) {
+        CU(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&p->ev_fork, &p->ev_flags, &p->ev_copy, &p->ev_run}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    char* S = (char*)p->stage;
+    auto at = [&](size_t o) -> void* { return o == (size_t)-1 ? nullptr : (void*)(S + o); };
+    cudaStream_t user = (cudaStream_t)stream, sc = p->s_copy, sr = p->s_run;
+    // ---- fork from the caller's stream (the PSF spectra may still be in flight there)
+    CU(cudaEventRecord(p->ev_fork, user));
+    CU(cudaStreamWaitEvent(sc, p->ev_fork, 0));
+    CU(cudaStreamWaitEvent(sr, p->ev_fork, 0));
+    // ---- run stream: small inputs, cleared outputs and flags, then the kernel
+    if (!in->bkg_is_image) CU(cudaMemcpyAsync(at(o_bkg), in->bkg, B * p->elem, cudaMemcpyHostToDevice, sr));
+    if (in->flux) CU(cudaMemcpyAsync(at(o_flux), in->flux, B * 8, cudaMemcpyHostToDevice, sr));
+    if (in->beta0) CU(cudaMemcpyAsync(at(o_b0), in->beta0, B * 8, cudaMemcpyHostToDevice, sr));
+    if (in->order) CU(cudaMemcpyAsync(at(o_ord), in->order, B * 4, cudaMemcpyHostToDevice, sr));
+    CU(cudaMemsetAsync(S + o_small, 0, off - o_small, sr));
+    CU(cudaMemsetAsync(p->ready, 0, B * sizeof(int), sr));
+    CU(cudaEventRecord(p->ev_flags, sr));
+    CU(cudaStreamWaitEvent(sc, p->ev_flags, 0));                   // no flag may be raised before the flags are cleared
+    bsgp_inputs di = {at(o_gn), at(o_bkg), in->bkg_is_image, (const double*)at(o_flux), (const double*)at(o_b0), at(o_x0), at(o_obj), (const int*)at(o_ord)};
+    bsgp_outputs dout = {(pin_mode & 1) ? at(o_xs) : x_mapped, (int*)at(o_it), (int*)at(o_st), (double*)at(o_di), (double*)at(o_ti), (double*)at(o_sv), (double*)at(o_er),
+                         (double*)at(o_bf), (int*)at(o_pe), (int*)at(o_lt), (double*)at(o_sc), (double*)at(o_ta), (double*)at(o_tl), (double*)at(o_tb),
+                         (int*)at(o_tt), (int*)at(o_te)};
+    const bool per_item = !p->frame && (img >= 65536 || in->order == nullptr) && !(pin_mode & 2);
+    auto upload_all = [&]() -> int {
+        CU(cudaMemcpyAsync(at(o_gn), in->gn, B * img, cudaMemcpyHostToDevice, sc));
+        if (in->bkg_is_image) CU(cudaMemcpyAsync(at(o_bkg), in->bkg, B * img, cudaMemcpyHostToDevice, sc));
+        if (in->x0) CU(cudaMemcpyAsync(at(o_x0), in->x0, B * img, cudaMemcpyHostToDevice, sc));
+        if (in->obj) CU(cudaMemcpyAsync(at(o_obj), in->obj, B * img, cudaMemcpyHostToDevice, sc));
+        return BSGP_OK;
+    };
+    int rc;
+    if (p->frame) {                                                // the frame kernel has no queue: everything resident first
+        rc = upload_all(); if (rc) return rc;
+        CU(cudaEventRecord(p->ev_copy, sc));
+        CU(cudaStreamWaitEvent(sr, p->ev_copy, 0));
+    }
+    rc = solve_checked(p, prm, batch, &di, &dout, sr, p->ready);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
+    // ---- copy stream: images in queue order, flags behind them.  From here on the kernel is waiting for flags: on any
+    // error every flag is raised before returning, so the kernel always terminates.
+    auto feed = [&]() -> int {
+        if (!per_item) {
+            rc = upload_all(); if (rc) return rc;
+            CU(cudaMemcpyAsync(p->ready, p->ones_host, B * sizeof(int), cudaMemcpyHostToDevice, sc));
+        } else {
+            // consecutive queue items that are also consecutive in memory travel as one copy of <= ~1 MB per array
+            const size_t max_run = img >= ((size_t)1 << 20) ? 1 : (((size_t)1 << 20) / img);
+            int i0 = 0;
+            while (i0 < batch) {
+                const int first = in->order ? in->order[i0] : i0;
+                int n = 1;
+                while (i0 + n < batch && (size_t)n < max_run && (in->order ? in->order[i0 + n] : i0 + n) == first + n) ++n;
+                const size_t o = (size_t)first * img, nb = (size_t)n * img;
+                CU(cudaMemcpyAsync((char*)at(o_gn) + o, (const char*)in->gn + o, nb, cudaMemcpyHostToDevice, sc));
+                if (in->bkg_is_image) CU(cudaMemcpyAsync((char*)at(o_bkg) + o, (const char*)in->bkg + o, nb, cudaMemcpyHostToDevice, sc));
+                if (in->x0) CU(cudaMemcpyAsync((char*)at(o_x0) + o, (const char*)in->x0 + o, nb, cudaMemcpyHostToDevice, sc));
+                if (in->obj) CU(cudaMemcpyAsync((char*)at(o_obj) + o, (const char*)in->obj + o, nb, cudaMemcpyHostToDevice, sc));
+                CU(cudaMemcpyAsync(p->ready + i0, p->ones_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, sc));
+                i0 += n;
+            }
+        }
+        return BSGP_OK;
+    };
+    if (!p->frame) {
+        rc = feed();
+        if (rc) {
+            cudaGetLastError();
+            cudaMemcpyAsync(p->ready, p->ones_host, B * sizeof(int), cudaMemcpyHostToDevice, sc);
+            cudaDeviceSynchronize();
+            return rc;
+        }
+    }
+    // ---- small outputs behind the kernel
+    auto down = [&](void* h, size_t o, size_t bytes) -> int { if (h && o != (size_t)-1) CU(cudaMemcpyAsync(h, S + o, bytes, cudaMemcpyDeviceToHost, sr)); return BSGP_OK; };
+    if (pin_mode & 1) TRY(down(out->x, o_xs, B * img));
+    TRY(down(out->iters, o_it, B * 4)); TRY(down(out->status, o_st, B * 4)); TRY(down(out->discr, o_di, B * tr * 8)); TRY(down(out->times, o_ti, B * tr * 8));
+    TRY(down(out->stop_value, o_sv, B * tr * 8)); TRY(down(out->err, o_er, B * (tr + 1) * 8)); TRY(down(out->beta_final, o_bf, B * 8));
+    TRY(down(out->proj_evals, o_pe, B * 4)); TRY(down(out->ls_trials, o_lt, B * 4)); TRY(down(out->scalars, o_sc, B * BSGP_NSCALARS * 8));
+    TRY(down(out->trace_alpha, o_ta, B * tr * 8)); TRY(down(out->trace_lambda, o_tl, B * tr * 8)); TRY(down(out->trace_beta, o_tb, B * tr * 8));
+    TRY(down(out->trace_trials, o_tt, B * tr * 4)); TRY(down(out->trace_evals, o_te, B * tr * 4));
+    // ---- join: the caller's stream continues after both private streams; results are complete when this returns
+    CU(cudaEventRecord(p->ev_copy, sc));
+    CU(cudaEventRecord(p->ev_run, sr));
+    CU(cudaStreamWaitEvent(user, p->ev_copy, 0));
+    CU(cudaStreamWaitEvent(user, p->ev_run, 0));
+    cudaError_t e = cudaStreamSynchronize(sc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sr);
+    if (e != cudaSuccess) return fail(BSGP_E_CUDA, "pipelined solve failed: %s", cudaGetErrorString(e));
     return BSGP_OK;
 }
 

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
         const int item = next_item(ctx, a.queue);
         if (item >= a.batch) break;
         const int img = a.order ? a.order[item] : item;
+        if (a.ready) wait_ready(a.ready + item);
         cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
         cplx<T>* tfa = a.tf_adj ? a.tf_adj + (a.n_psf > 1 ? (size_t)img * tf_stride : 0) : tf;
         solve_image<T, MK>(ctx, a, S, buf, tf, tfa, img);

@@ -50,6 +50,7 @@ template <typename T> struct SolveArgs {
     double* beta_final; int* proj_evals; int* ls_trials; double* scalars;
     double* tr_alpha; double* tr_lambda; double* tr_beta; int* tr_trials; int* tr_evals;
     int* queue;
+    const int* ready;               // [batch] or NULL: queue item i may start once ready[i] != 0 (pipelined upload, bsgp_solve_batch_pinned)
 };
 
 // Per-image constants of one CTA (shared memory).  Pointers address this CTA's slab of each array.

@@ -190,18 +190,24 @@ def _params(divergence, kw, has_flux):
 
 
 def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=None, obj=None, dtype="float64",
-                device=0, trace=False, plan=None, psf_is_set=False, padded=False, **kw):
+                device=0, trace=False, plan=None, psf_is_set=False, padded=False, x_out=None, **kw):
     """Restore a batch of independent images in one persistent kernel launch.
 
     gn [B,ny,nx]; psf [ny,nx] (shared) or [B,ny,nx]; bkg scalar, [B] or [B,ny,nx]; flux None or [B];
     betaParam scalar or [B].  Keyword arguments are those of sgp()/sgp_betaDiv() (sgp.py:41-47,
     506-513).  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (asynchronous on the
-    current stream).  ``padded=True`` selects the zero-padded operator of use_original_SGP_Afunction=False
+    current stream); PINNED CPU tensors in -> pinned CPU tensors out through the pipelined host path
+    (upload, solve and download overlap; see bsgp_solve_batch_pinned in include/bsgp.h; ``x_out`` may name a
+    pinned tensor that receives the restored images, so that a caller in a loop reuses its buffer).  ``padded=True`` selects the zero-padded operator of use_original_SGP_Afunction=False
     (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size."""
     if divergence not in ("kl", "beta"):
         raise ValueError("divergence must be 'kl' or 'beta'")
+    if x_out is not None and not (_is_tensor(gn) and not gn.is_cuda and gn.is_pinned()):
+        raise ValueError("x_out is only supported with pinned CPU tensor inputs")
     if padded:
         return _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw)
+    if _is_tensor(gn) and not gn.is_cuda and gn.is_pinned():
+        return _solve_batch_pinned(gn, psf, bkg, divergence, flux, betaParam, x0, obj, device, trace, plan, psf_is_set, x_out, kw)
     if _is_tensor(gn):
         return _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw)
     npdt = _NP[dtype]
@@ -358,6 +364,80 @@ def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trac
         res = BatchResult(trace=tr, **out)
         res._keepalive = (gn, bkg_t, fl, b0, x0t, objt, order)
     return res
+
+
+def _solve_batch_pinned(gn, psf, bkg, divergence, flux, betaParam, x0, obj, device, trace, plan, psf_is_set, x_out, kw):
+    """Page-locked CPU tensors -> page-locked CPU tensors; one call of bsgp_solve_batch_pinned (returns when the results
+    are in host memory).  `device` selects the GPU.  Image-shaped arguments (bkg stack, x0, obj) must be pinned too."""
+    import torch
+    dtype = {torch.float64: "float64", torch.float32: "float32"}[gn.dtype]
+    npdt = _NP[dtype]
+    gn = gn.contiguous()
+    if gn.dim() != 3:
+        raise ValueError("gn must be [batch, ny, nx]")
+    B, ny, nx = gn.shape
+    p = _params(divergence, kw, flux is not None)
+    plan = plan or get_plan(ny, nx, dtype, device)
+    with torch.cuda.device(plan.device):
+        if not psf_is_set:
+            psf_t = psf if _is_tensor(psf) else torch.as_tensor(np.ascontiguousarray(psf))
+            n_psf = plan.set_psf(psf_t.to(device=f"cuda:{plan.device}", dtype=gn.dtype, non_blocking=True))
+            if n_psf not in (1, B):
+                raise ValueError("psf must be one image or one per batch entry")
+
+        def pinned_image(t, name):
+            if t is None:
+                return None
+            if not (_is_tensor(t) and not t.is_cuda and t.is_pinned() and t.dtype == gn.dtype and tuple(t.shape) == tuple(gn.shape)):
+                raise ValueError(f"{name} must be a pinned CPU tensor of the shape and dtype of gn")
+            return t.contiguous()
+
+        if _is_tensor(bkg) and bkg.dim() == 3:
+            bkg_img, bkg_t = 1, pinned_image(bkg, "bkg")
+            bkg_ptr = bkg_t.data_ptr()
+        else:
+            bkg_img, bkg_t = 0, np.ascontiguousarray(np.broadcast_to(np.asarray(bkg, dtype=npdt).reshape(-1), (B,)).astype(npdt))
+            bkg_ptr = bkg_t.ctypes.data
+
+        def small(a):
+            return None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1), (B,)))
+
+        fl, b0 = small(flux), small(betaParam)
+        x0t, objt = pinned_image(x0, "x0"), pinned_image(obj, "obj")
+        if p.init_recon == 1 and x0t is None:
+            raise ValueError("init_recon=1 needs x0 (the sgp()/sgp_betaDiv() wrappers draw it with seed 42)")
+        T = p.maxit + 1
+        if x_out is None:
+            x = torch.empty((B, ny, nx), dtype=gn.dtype, pin_memory=True)
+        else:
+            x = x_out
+            if not (_is_tensor(x) and not x.is_cuda and x.is_pinned() and x.dtype == gn.dtype and tuple(x.shape) == (B, ny, nx) and x.is_contiguous()):
+                raise ValueError("x_out must be a contiguous pinned CPU tensor of the shape and dtype of gn")
+
+        # the small outputs are page-locked as well (torch's caching host allocator makes repeated calls cheap), handed
+        # back as numpy views: the copies behind the kernel run at full PCIe speed and never block on a staging buffer
+        def hbuf(shape, dt=np.float64):
+            return torch.empty(shape, dtype=torch.float64 if dt is np.float64 else torch.int32, pin_memory=True).numpy()
+
+        out = dict(iters=hbuf(B, np.int32), status=hbuf(B, np.int32), discr=hbuf((B, T)), times=hbuf((B, T)),
+                   stop_value=hbuf((B, T)), err=hbuf((B, T + 1)) if p.errflag else None, beta_final=hbuf(B),
+                   proj_evals=hbuf(B, np.int32), ls_trials=hbuf(B, np.int32), scalars=hbuf((B, _capi.NSCALARS)))
+        tr = None
+        if trace:
+            tr = dict(alpha=hbuf((B, T)), lam=hbuf((B, T)), beta=hbuf((B, T)), trials=hbuf((B, T), np.int32), evals=hbuf((B, T), np.int32))
+
+        def ptr(a):
+            return None if a is None else (a.data_ptr() if _is_tensor(a) else a.ctypes.data)
+
+        order = _queue_order(divergence, b0)
+        ci = _capi.Inputs(gn.data_ptr(), bkg_ptr, bkg_img, ptr(fl), ptr(b0), ptr(x0t), ptr(objt), ptr(order))
+        co = _capi.Outputs(x.data_ptr(), ptr(out["iters"]), ptr(out["status"]), ptr(out["discr"]), ptr(out["times"]),
+                           ptr(out["stop_value"]), ptr(out["err"]), ptr(out["beta_final"]), ptr(out["proj_evals"]),
+                           ptr(out["ls_trials"]), ptr(out["scalars"]),
+                           ptr(tr["alpha"]) if tr else None, ptr(tr["lam"]) if tr else None, ptr(tr["beta"]) if tr else None,
+                           ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
+        check(lib().bsgp_solve_batch_pinned(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co), _stream_ptr()))
+    return BatchResult(x=x, trace=tr, **out)
 
 
 def project_batch(b, c, dia, sat_cap=None, lambda_=0.0, dlambda_=1.0, tol_lam=1e-11, max_projs=1000, device=0):

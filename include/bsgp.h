@@ -141,6 +141,15 @@ int bsgp_solve_batch(bsgp_plan* plan, const bsgp_params* params, int batch, cons
                      const bsgp_outputs* out_dev, void* stream);
 int bsgp_solve_batch_host(bsgp_plan* plan, const bsgp_params* params, int batch, const bsgp_inputs* in_host,
                           const bsgp_outputs* out_host);
+/* The same call for PAGE-LOCKED host images (in.gn, in.bkg if it is an image stack, in.x0, in.obj, out.x; the small
+ * arrays may live in any host memory), pipelined: the images are uploaded on a private copy stream in the order the
+ * work queue hands them out while the persistent kernel is already restoring the first ones (it waits for a per-item
+ * ready flag), and every restored image is stored straight into out.x (mapped, zero-copy) while others are still being
+ * solved.  Ordered after the work already queued on `stream` (e.g. bsgp_set_psf); returns when all results are in host
+ * memory.  This is what replaces the reference's per-image Python loop when the caller's data lives on the host
+ * (application_sgp_star_stamps.py:56-105, application_sgp_subdivisions.py:83-107). */
+int bsgp_solve_batch_pinned(bsgp_plan* plan, const bsgp_params* params, int batch, const bsgp_inputs* in_host,
+                            const bsgp_outputs* out_host, void* stream);
 
 /* y = real(ifftn(TF * fftn(x))) (adjoint = 0) or with conj(TF) (adjoint = 1) for `batch` images: the
  * reference's A / A^T closures (sgp.py:111-120). PSF index = image index if n_psf > 1. */

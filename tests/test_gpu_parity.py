@@ -467,3 +467,44 @@ def test_padded_operator_device_tensors(bs):
     torch.cuda.synchronize()
     assert t.x.shape == (3, 45, 61)
     assert np.array_equal(t.x.cpu().numpy(), a.x) and np.array_equal(t.iters.cpu().numpy(), a.iters)
+
+
+def test_pipelined_pinned_path_matches_numpy_path(bs, fixtures, golden):
+    """Page-locked CPU tensors go through bsgp_solve_batch_pinned (per-item upload behind ready flags, zero-copy
+    output): same bits as the plain host path.  Covers: permuted queue + image background (per-item copies), small
+    images with a permuted queue (whole-array upload), small images without a queue order (contiguous runs), x0."""
+    import torch
+    # tiles: 2-D background, shared PSF, 5 beta values -> permuted queue, one copy per item
+    gn = np.stack([fixtures[f"tile{(i // 5) * 5}/gn"] for i in range(10)])
+    bk = np.stack([fixtures[f"tile{(i // 5) * 5}/bkg"] for i in range(10)])
+    names = [f"tile{i:02d}" for i in range(10)]
+    flux = np.array([float(golden[n + "/flux_in"]) for n in names])
+    b0 = np.array([float(golden[n + "/beta0"]) for n in names])
+    a = bs.solve_batch(gn, fixtures["tile0/psf"], bk, divergence="beta", flux=flux, betaParam=b0, trace=True, **bs.synth.TILE_KWARGS)
+    for rep in range(2):          # the second call reuses the staging arena and the flags
+        xo = torch.empty(gn.shape, dtype=torch.float64).pin_memory() if rep else None      # caller-owned output buffer
+        p = bs.solve_batch(torch.as_tensor(gn).pin_memory(), fixtures["tile0/psf"], torch.as_tensor(bk).pin_memory(), divergence="beta",
+                           flux=flux, betaParam=b0, trace=True, x_out=xo, **bs.synth.TILE_KWARGS)
+        assert p.x.is_pinned() and np.array_equal(p.x.numpy(), a.x) and (xo is None or p.x is xo)
+        assert np.array_equal(p.iters, a.iters) and np.array_equal(p.discr, a.discr) and np.array_equal(p.status, a.status)
+        assert np.array_equal(p.proj_evals, a.proj_evals) and np.array_equal(p.trace["alpha"], a.trace["alpha"])
+    # stamps: per-stamp PSF, scalar backgrounds; permuted queue (beta varies) and natural order (one beta)
+    gn = np.stack([fixtures[f"stamp{i}/gn"] for i in range(16)])
+    psf = np.stack([fixtures[f"stamp{i}/psf"] for i in range(16)])
+    bkg = np.array([float(fixtures[f"stamp{i}/bkg"]) for i in range(16)])
+    flux = np.array([float(golden[f"stamp{i:02d}/flux_in"]) for i in range(16)])
+    for b0 in (np.array([float(golden[f"stamp{i:02d}/beta0"]) for i in range(16)]), 1.005):
+        a = bs.solve_batch(gn, psf, bkg, divergence="beta", flux=flux, betaParam=b0, **bs.synth.STAMP_KWARGS)
+        p = bs.solve_batch(torch.as_tensor(gn).pin_memory(), psf, bkg, divergence="beta", flux=flux, betaParam=b0, **bs.synth.STAMP_KWARGS)
+        assert np.array_equal(p.x.numpy(), a.x) and np.array_equal(p.iters, a.iters) and np.array_equal(p.beta_final, a.beta_final)
+    # KL, random start image (init_recon = 1): x0 travels with the images
+    g1, psf1, bkg1 = fixtures["ngc/gn"], fixtures["ngc/psf"], np.float64(fixtures["ngc/bkg"])
+    kw = dict(init_recon=1, stop_criterion=1, MAXIT=5)
+    np.random.seed(42)
+    x0 = np.random.randn(2, *g1.shape)
+    gg = np.stack([g1, g1])
+    a = bs.solve_batch(gg, psf1, bkg1, divergence="kl", x0=x0, **kw)
+    p = bs.solve_batch(torch.as_tensor(gg).pin_memory(), psf1, bkg1, divergence="kl", x0=torch.as_tensor(x0).pin_memory(), **kw)
+    assert np.array_equal(p.x.numpy(), a.x) and np.array_equal(p.discr, a.discr)
+    with pytest.raises(ValueError):
+        bs.solve_batch(torch.as_tensor(gg).pin_memory(), psf1, bkg1, divergence="kl", x0=torch.as_tensor(x0), **kw)
