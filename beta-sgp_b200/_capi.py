@@ -14,12 +14,13 @@ LIB_PATH = os.environ.get("BSGP_LIB") or os.path.join(_HERE, "csrc", "libbsgp.so
 
 BSGP_F64, BSGP_F32 = 0, 1
 DIV_KL, DIV_BETA = 0, 1
-ST_OK, ST_BAD_FLUX, ST_EMPTY_BOUNDS, ST_PROJ_NO_BRACKET = 0, 1, 2, 3
+ST_OK, ST_BAD_FLUX, ST_EMPTY_BOUNDS, ST_PROJ_NO_BRACKET, ST_INPUT_TIMEOUT = 0, 1, 2, 3, 4
 NSCALARS = 8
 STATUS_TEXT = {
     ST_BAD_FLUX: "non-positive or non-finite flux with proj_type=1",
     ST_EMPTY_BOUNDS: "no positive entry in flux/(flux+bkg)*AT(gn): scaling-matrix bounds undefined",
     ST_PROJ_NO_BRACKET: "flux-conserving projection could not bracket the multiplier",
+    ST_INPUT_TIMEOUT: "pipelined upload of the image did not arrive (bsgp_solve_batch_pinned)",
 }
 
 

@@ -25,7 +25,8 @@ struct SharedCtl {
     double inbox[2][kMaxG][kMaxK];
     unsigned long long mbar[2];     // transaction barriers of the two inbox halves (cluster all-reduce)
     int next_img;
-    int pad[3];
+    int ready_verdict;
+    int pad[2];
 };
 
 __device__ __forceinline__ double red_combine(int op, double a, double b) {
@@ -198,35 +199,42 @@ __device__ __forceinline__ GridCtx make_grid_ctx(SharedCtl* sh, double* gpart) {
     return c;
 }
 
-// next work item for the whole cluster (leader claims it, pushes it into every CTA's shared memory)
-__device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue) {
+// Pipelined ingest (bsgp_solve_batch_pinned): the copy engine writes an image into the staging buffer and then its
+// flag; the cluster leader polls the flag with a system-scope acquire load before anybody reads the image (the cluster
+// barrier of next_item passes the acquire on to the other CTAs).  A flag that does not arrive within 20 s (a failed
+// upload) makes the cluster skip the image with BSGP_ST_INPUT_TIMEOUT instead of spinning forever.
+__device__ __forceinline__ int poll_ready(const int* flag) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v) break;
+        __nanosleep(400);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) break;
+    }
+    return v != 0;
+}
+
+// next work item for the whole cluster (leader claims it, waits for its upload if there is one, and pushes the item and
+// the verdict into every CTA's shared memory).  *ready_ok = false: the item's inputs never arrived.
+__device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue, const int* ready, int batch, bool* ready_ok) {
     if (ctx.rank == 0 && ctx.tid == 0) {
         const int v = atomicAdd(queue, 1);
+        const int ok = (ready && v < batch) ? poll_ready(ready + v) : 1;
         if (ctx.G > 1) {
             cg::cluster_group cl = cg::this_cluster();
-            for (int r = 0; r < ctx.G; ++r) *cl.map_shared_rank(&ctx.sh->next_img, r) = v;
+            for (int r = 0; r < ctx.G; ++r) { *cl.map_shared_rank(&ctx.sh->next_img, r) = v; *cl.map_shared_rank(&ctx.sh->ready_verdict, r) = ok; }
         } else {
-            ctx.sh->next_img = v;
+            ctx.sh->next_img = v; ctx.sh->ready_verdict = ok;
         }
     }
     ctx.cluster_sync();
     const int img = ctx.sh->next_img;
+    *ready_ok = ctx.sh->ready_verdict != 0;
     ctx.cluster_sync();          // nobody may still be reading when the leader claims the next one
     return img;
-}
-
-// Pipelined ingest (bsgp_solve_batch_pinned): the copy engine writes an image into the staging buffer and then its
-// flag; the CTA polls the flag with a system-scope acquire load before its first read of the image.
-__device__ __forceinline__ void wait_ready(const int* flag) {
-    if (threadIdx.x == 0) {
-        int v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v) break;
-            __nanosleep(400);
-        }
-    }
-    __syncthreads();
 }
 
 // dynamic shared memory layout of the persistent kernels (byte offsets, computed by the host)

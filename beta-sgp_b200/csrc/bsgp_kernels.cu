@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
     cplx<T>* spec = a.spec + (size_t)cluster_id * a.spec_stride;
     const int r0 = ctx.rank * a.g.rows_per_cta;
     for (;;) {
-        const int img = next_item(ctx, a.queue);
+        bool ready_ok;
+        const int img = next_item(ctx, a.queue, nullptr, a.count, &ready_ok);
         if (img >= a.count) break;
         const T* src = a.in + (size_t)img * npix;
         if (a.mode == CONV_MAKE_TF) {
@@ -820,10 +821,7 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
         CU(cudaEventRecord(p->ev_copy, sc));
         CU(cudaStreamWaitEvent(sr, p->ev_copy, 0));
     }
-    rc = solve_checked(p, prm, batch, &di, &dout, sr, p->ready);
-    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
-    // ---- copy stream: images in queue order, flags behind them.  From here on the kernel is waiting for flags: on any
-    // error every flag is raised before returning, so the kernel always terminates.
+    // ---- copy stream: images in queue order, flags behind them
     auto feed = [&]() -> int {
         if (!per_item) {
             rc = upload_all(); if (rc) return rc;
@@ -849,13 +847,12 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
     };
     if (!p->frame) {
         rc = feed();
-        if (rc) {
-            cudaGetLastError();
-            cudaMemcpyAsync(p->ready, p->ones_host, B * sizeof(int), cudaMemcpyHostToDevice, sc);
-            cudaDeviceSynchronize();
-            return rc;
-        }
+        if (rc) { cudaGetLastError(); cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
     }
+    // ---- run stream: the kernel.  Launched AFTER the copies are queued, so that a launch made synchronous by a tool
+    // (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING) cannot wait for flags that nobody has been asked to raise yet.
+    rc = solve_checked(p, prm, batch, &di, &dout, sr, p->ready);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
     // ---- small outputs behind the kernel
     auto down = [&](void* h, size_t o, size_t bytes) -> int { if (h && o != (size_t)-1) CU(cudaMemcpyAsync(h, S + o, bytes, cudaMemcpyDeviceToHost, sr)); return BSGP_OK; };
     if (pin_mode & 1) TRY(down(out->x, o_xs, B * img));

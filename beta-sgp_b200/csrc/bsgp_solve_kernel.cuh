@@ -52,10 +52,14 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
     }
     __syncthreads();
     for (;;) {
-        const int item = next_item(ctx, a.queue);
+        bool ready_ok;
+        const int item = next_item(ctx, a.queue, a.ready, a.batch, &ready_ok);
         if (item >= a.batch) break;
         const int img = a.order ? a.order[item] : item;
-        if (a.ready) wait_ready(a.ready + item);
+        if (!ready_ok) {                                   // upload never arrived: report and skip (cluster-uniform)
+            if (ctx.rank == 0 && ctx.tid == 0) { a.status[img] = BSGP_ST_INPUT_TIMEOUT; a.iters[img] = 0; }
+            continue;
+        }
         cplx<T>* tf = a.tf + (a.n_psf > 1 ? (size_t)img * tf_stride : 0);
         cplx<T>* tfa = a.tf_adj ? a.tf_adj + (a.n_psf > 1 ? (size_t)img * tf_stride : 0) : tf;
         solve_image<T, MK>(ctx, a, S, buf, tf, tfa, img);

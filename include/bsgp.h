@@ -36,7 +36,8 @@ enum { BSGP_OK = 0, BSGP_E_ARG = 1, BSGP_E_SHAPE = 2, BSGP_E_CUDA = 3, BSGP_E_NO
 enum { BSGP_ST_OK = 0,
        BSGP_ST_BAD_FLUX = 1,        /* flux <= 0 or non-finite with proj_type = 1 (reference: ValueError at sgp.py:269/713) */
        BSGP_ST_EMPTY_BOUNDS = 2,    /* no positive entry in flux/(flux+bkg)*A^T(gn) (reference: ValueError at sgp.py:269/713) */
-       BSGP_ST_PROJ_NO_BRACKET = 3  /* projection could not bracket the multiplier (reference: endless loop) */ };
+       BSGP_ST_PROJ_NO_BRACKET = 3, /* projection could not bracket the multiplier (reference: endless loop) */
+       BSGP_ST_INPUT_TIMEOUT = 4    /* bsgp_solve_batch_pinned: the image's upload did not arrive within 20 s; image skipped */ };
 
 /* Keyword arguments of sgp() / sgp_betaDiv(), same names and meaning (sgp.py:41-47, 506-513). */
 typedef struct bsgp_params {
