@@ -201,6 +201,46 @@ __global__ void __launch_bounds__(256) bsgp_betagrad_kernel(const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tiling of a frame into overlapping subdivisions and re-assembly (reference: utils.py:332-389 create_subdivisions /
+// calculate_slice_bboxes, utils.py:392-397 reconstruct_full_image_from_patches).  Pure data movement, HBM-bound:
+// every thread moves one pixel, consecutive threads consecutive columns (tile origins are arbitrary, so rows are
+// not 16-byte aligned in general); grids are sized in multiples of the SM count.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bsgp_extract_tiles_kernel(const T* __restrict__ frame, int height, int width, const int* __restrict__ origins, int n, int th, int tw, T* __restrict__ tiles) {
+    const size_t per = (size_t)th * tw, total = per * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e / per);
+        const int r = (int)((e - (size_t)t * per) / tw), c = (int)(e - (size_t)t * per - (size_t)r * tw);
+        const int y = origins[2 * t] + r, x = origins[2 * t + 1] + c;
+        tiles[e] = (y >= 0 && y < height && x >= 0 && x < width) ? frame[(size_t)y * width + x] : (T)0;
+    }
+}
+
+// out(y, x) = sum_t w_t tile_t / sum_t w_t over the tiles covering the pixel, in tile order (deterministic), with
+// w_t = ramp(dy) * ramp(dx), ramp(d) = min(d + 1, size - d, feather): a linear cross-fade over `feather` pixels at
+// tile borders (feather <= 1: plain average of the overlapping tiles).  Pixels covered by no tile get 0.
+template <typename T>
+__global__ void bsgp_assemble_tiles_kernel(const T* __restrict__ tiles, const int* __restrict__ origins, int n, int th, int tw, int feather, T* __restrict__ frame, int height, int width) {
+    const size_t total = (size_t)height * width, per = (size_t)th * tw;
+    const int f = feather < 1 ? 1 : feather;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(e / width), x = (int)(e - (size_t)y * width);
+        double num = 0.0, den = 0.0;
+        for (int t = 0; t < n; ++t) {
+            const int dy = y - origins[2 * t], dx = x - origins[2 * t + 1];
+            if (dy < 0 || dy >= th || dx < 0 || dx >= tw) continue;
+            int wy = dy + 1 < th - dy ? dy + 1 : th - dy; wy = wy < f ? wy : f;
+            int wx = dx + 1 < tw - dx ? dx + 1 : tw - dx; wx = wx < f ? wx : f;
+            const double w = (double)wy * (double)wx;
+            num += w * (double)tiles[(size_t)t * per + (size_t)dy * tw + dx];
+            den += w;
+        }
+        frame[e] = den > 0.0 ? (T)(num / den) : (T)0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -971,5 +1011,67 @@ int bsgp_beta_grad_terms_host(const double* den, const double* gn, long long n, 
     return BSGP_OK;
 }
 #undef TRY
+
+// ------------------------------------------------------------------------------------------------
+// tiling (utils.py:332-397)
+// ------------------------------------------------------------------------------------------------
+int bsgp_tile_boxes(int height, int width, int tile_h, int tile_w, double overlap_h_ratio, double overlap_w_ratio, int* boxes_xyxy, int max_boxes, int* n_boxes) {
+    if (!n_boxes || height < 1 || width < 1 || tile_h < 1 || tile_w < 1) return fail(BSGP_E_ARG, "bad argument");
+    // utils.py:360-375: rows outer, columns inner; step = tile - int(ratio * tile); a tile that would stick out is
+    // shifted back inside (clamped at 0 when the image is smaller than the tile)
+    const int oy = (int)(overlap_h_ratio * (double)tile_h), ox = (int)(overlap_w_ratio * (double)tile_w);
+    if (oy >= tile_h || ox >= tile_w || oy < 0 || ox < 0) return fail(BSGP_E_ARG, "overlap must be smaller than the tile");
+    int n = 0;
+    for (int y0 = 0;; y0 += tile_h - oy) {
+        const int y1 = y0 + tile_h;
+        for (int x0 = 0;; x0 += tile_w - ox) {
+            const int x1 = x0 + tile_w;
+            int bx0 = x0, by0 = y0, bx1 = x1, by1 = y1;
+            if (y1 > height || x1 > width) {
+                bx1 = x1 < width ? x1 : width; by1 = y1 < height ? y1 : height;
+                bx0 = bx1 - tile_w > 0 ? bx1 - tile_w : 0; by0 = by1 - tile_h > 0 ? by1 - tile_h : 0;
+            }
+            if (boxes_xyxy && n < max_boxes) { int* b = boxes_xyxy + 4 * (size_t)n; b[0] = bx0; b[1] = by0; b[2] = bx1; b[3] = by1; }
+            ++n;
+            if (x1 >= width) break;
+        }
+        if (y1 >= height) break;
+    }
+    *n_boxes = n;
+    if (boxes_xyxy && n > max_boxes) return fail(BSGP_E_ARG, "%d boxes needed, room for %d", n, max_boxes);
+    return BSGP_OK;
+}
+
+static int tile_grid(int device, size_t total, int* blocks) {
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    size_t want = (total + 255) / 256, cap = (size_t)sms * 8;          // 8 CTAs of 256 threads per SM, grid-stride beyond
+    *blocks = (int)(want < cap ? (want ? want : 1) : cap);
+    return BSGP_OK;
+}
+
+int bsgp_extract_tiles(const void* frame_dev, int height, int width, int dtype, const int* origins_dev, int n, int tile_h, int tile_w, void* tiles_dev, int device, void* stream) {
+    if (!frame_dev || !origins_dev || !tiles_dev || n < 1 || tile_h < 1 || tile_w < 1 || height < 1 || width < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "bad dtype");
+    CU(cudaSetDevice(device));
+    int blocks = 0, rc = tile_grid(device, (size_t)n * tile_h * tile_w, &blocks);
+    if (rc) return rc;
+    if (dtype == BSGP_F64) bsgp_extract_tiles_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)frame_dev, height, width, origins_dev, n, tile_h, tile_w, (double*)tiles_dev);
+    else bsgp_extract_tiles_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)frame_dev, height, width, origins_dev, n, tile_h, tile_w, (float*)tiles_dev);
+    CU(cudaGetLastError());
+    return BSGP_OK;
+}
+
+int bsgp_assemble_tiles(const void* tiles_dev, const int* origins_dev, int n, int tile_h, int tile_w, int dtype, int feather, void* frame_dev, int height, int width, int device, void* stream) {
+    if (!frame_dev || !origins_dev || !tiles_dev || n < 1 || tile_h < 1 || tile_w < 1 || height < 1 || width < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "bad dtype");
+    CU(cudaSetDevice(device));
+    int blocks = 0, rc = tile_grid(device, (size_t)height * width, &blocks);
+    if (rc) return rc;
+    if (dtype == BSGP_F64) bsgp_assemble_tiles_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (double*)frame_dev, height, width);
+    else bsgp_assemble_tiles_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (float*)frame_dev, height, width);
+    CU(cudaGetLastError());
+    return BSGP_OK;
+}
 
 }  // extern "C"

@@ -176,6 +176,20 @@ int bsgp_beta_div_host(const double* y, const double* x, long long n, double bet
 int bsgp_beta_grad_terms_host(const double* den, const double* gn, long long n, double beta, double* p1, double* u,
                               int device);
 
+/* Tiling of a frame into overlapping subdivisions and re-assembly: the callers either side of the batched solve
+ * (utils.py:332-375 calculate_slice_bboxes, :378-389 create_subdivisions, :392-397 reconstruct_full_image_from_patches).
+ * bsgp_tile_boxes (host): the reference's enumeration, boxes as [xmin, ymin, xmax, ymax]; boxes_xyxy may be NULL to
+ * query the count.  bsgp_extract_tiles: tiles[t] = frame[y0:y0+tile_h, x0:x0+tile_w] for origins[t] = (y0, x0), zeros
+ * outside the frame.  bsgp_assemble_tiles: weighted average of the tiles covering each pixel with a linear cross-fade
+ * of `feather` pixels at tile borders (<= 1: plain average); replaces reproject_and_coadd, which needs WCS headers
+ * and is not bit-comparable. */
+int bsgp_tile_boxes(int height, int width, int tile_h, int tile_w, double overlap_h_ratio, double overlap_w_ratio,
+                    int* boxes_xyxy, int max_boxes, int* n_boxes);
+int bsgp_extract_tiles(const void* frame_dev, int height, int width, int dtype, const int* origins_dev, int n, int tile_h,
+                       int tile_w, void* tiles_dev, int device, void* stream);
+int bsgp_assemble_tiles(const void* tiles_dev, const int* origins_dev, int n, int tile_h, int tile_w, int dtype, int feather,
+                        void* frame_dev, int height, int width, int device, void* stream);
+
 int bsgp_device_count(void);
 const char* bsgp_last_error_string(void);
 const char* bsgp_version(void);

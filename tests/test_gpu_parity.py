@@ -508,3 +508,56 @@ def test_pipelined_pinned_path_matches_numpy_path(bs, fixtures, golden):
     assert np.array_equal(p.x.numpy(), a.x) and np.array_equal(p.discr, a.discr)
     with pytest.raises(ValueError):
         bs.solve_batch(torch.as_tensor(gg).pin_memory(), psf1, bkg1, divergence="kl", x0=torch.as_tensor(x0), **kw)
+
+
+def test_tiling_extract_assemble_and_frame_restoration(bs, fixtures, golden):
+    """tiles cut on the device equal numpy slices of the reference's boxes (bit-exact); re-assembly is
+    the documented cross-fade (checked against a numpy restatement; identity on consistent tiles); a frame made of four
+    golden tiles restored through restore_frame equals the four golden single-tile solves."""
+    import torch
+    rng = np.random.default_rng(5)
+    frame = rng.random((450, 375))
+    for shape, ov in (((128, 64), 13), ((100, 100), 10), ((512, 512), 0)):
+        tiles, org = bs.tiles.create_subdivisions(frame, shape, ov)
+        boxes = bs.tiles.calculate_slice_bboxes(450, 375, shape[0], shape[1], ov / shape[0], ov / shape[1])
+        assert len(boxes) == len(org)
+        th, tw = shape
+        t = tiles.cpu().numpy()
+        for k, (y0, x0) in enumerate(org):
+            assert (x0, y0) == (boxes[k][0], boxes[k][1])
+            want = np.zeros(shape)
+            sub = frame[y0:y0 + th, x0:x0 + tw]
+            want[:sub.shape[0], :sub.shape[1]] = sub                      # image smaller than the tile: zero fill
+            assert np.array_equal(t[k], want)
+        back = bs.tiles.reconstruct_full_image_from_patches(tiles, org, frame.shape).cpu().numpy()
+        assert np.abs(back - frame).max() <= 4e-16                        # weighted mean of equal values
+        # cross-fade against a numpy restatement, on tiles that disagree in their overlaps
+        noisy = t + rng.normal(0, 1e-3, t.shape)
+        f = 5
+        got = bs.tiles.reconstruct_full_image_from_patches(noisy, org, frame.shape, feather=f).cpu().numpy()
+        num = np.zeros(frame.shape); den = np.zeros(frame.shape)
+        ry = np.minimum(np.minimum(np.arange(th) + 1, th - np.arange(th)), f)
+        rx = np.minimum(np.minimum(np.arange(tw) + 1, tw - np.arange(tw)), f)
+        w = np.outer(ry, rx).astype(float)
+        for k, (y0, x0) in enumerate(org):
+            hh, ww = min(th, 450 - y0), min(tw, 375 - x0)
+            num[y0:y0 + hh, x0:x0 + ww] += (w * noisy[k])[:hh, :ww]
+            den[y0:y0 + hh, x0:x0 + ww] += w[:hh, :ww]
+        assert np.abs(got - num / den).max() <= 1e-14
+    # frame in -> frame out on a 512 x 512 mosaic of two golden tiles (beta of the golden cases tile00 / tile05)
+    g0, g5 = fixtures["tile0/gn"], fixtures["tile5/gn"]
+    b0, b5 = fixtures["tile0/bkg"], fixtures["tile5/bkg"]
+    mosaic = np.block([[g0, g5], [g5, g0]])
+    bkgmap = np.block([[b0, b5], [b5, b0]])
+    names = ["tile00", "tile05", "tile05", "tile00"]
+    beta = np.array([float(golden[n + "/beta0"]) for n in names])
+    out, res, org = bs.tiles.restore_frame(mosaic, fixtures["tile0/psf"], bkgmap, (256, 256), 0, betaParam=torch.as_tensor(beta, device="cuda:0"),
+                                           **{k: v for k, v in bs.synth.TILE_KWARGS.items() if k != "proj_type"})
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    for k, n in enumerate(names):
+        y0, x0 = org[k]
+        assert int(res.iters[k]) == int(golden[n + "/iters"]), n
+        xs = golden[n + "/x_sub"]                                          # x[::8, ::8] of the reference's restored tile
+        assert np.abs(out[y0:y0 + 256:8, x0:x0 + 256:8] - xs).max() <= 1e-8 * xs.max()
+        assert abs(out[y0:y0 + 256, x0:x0 + 256].sum() - float(golden[n + "/sum_x"])) <= 1e-9 * float(golden[n + "/sum_x"])

@@ -235,3 +235,19 @@ def test_emulated_padded_operator_matches_oracle(div, kw):
     pad = r["x"].copy()
     pad[geo.rows, geo.cols] = 0.0
     assert not pad.any()                                      # nothing leaks into the padding
+
+
+def test_tile_boxes_match_reference_golden():
+    """bsgp_tile_boxes (host index arithmetic, no GPU) against the outputs of the reference's calculate_slice_bboxes
+    (utils.py:332-375) committed by tests/golden/make_tiles_golden.py."""
+    import json
+    import beta_sgp_b200 as bs
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiles_golden.json")))
+    assert len(cases) >= 10
+    for c in cases:
+        assert bs.tiles.calculate_slice_bboxes(*c["args"]) == c["boxes"], c["args"]
+    # create_subdivisions' call shape (utils.py:381-384) and the synthetic workload's own enumeration agree
+    org = bs.tiles.tile_origins((2048, 2048), (256, 256), 0)
+    assert [tuple(o) for o in org.tolist()] == bs.synth.tile_boxes(2048, 2048, 256, 0)
+    with pytest.raises(bs._capi.BsgpError):
+        bs.tiles.calculate_slice_bboxes(100, 100, 10, 10, 1.0, 0.0)          # the reference would loop forever
