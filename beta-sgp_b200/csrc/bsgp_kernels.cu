@@ -243,6 +243,70 @@ __global__ void bsgp_assemble_tiles_kernel(const T* __restrict__ tiles, const in
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// PSF model evaluation (reference: psf/psf_calculate.py:52-111, PSF.calc_psf_pix / get_psf_mat / normalize_psf_mat): the
+// DIAPL model, a sum of `ngauss` elliptical Gaussians (widths in geometric progression) times a local polynomial of degree
+// 2 in (x, y).  One CTA evaluates one PSF on its (2 hw + 1)^2 support, sums it and writes it, optionally normalised to
+// sum 1, centred at (ny/2, nx/2) of an ny x nx image (zeros elsewhere): the placement the circular operator expects
+// (sgp.py:109, fftshift), so per-stamp PSFs are generated where they are used instead of being uploaded.
+// params row: cos, sin, ax, ay, sigma_inc, then ngauss * 6 coefficients.  Operand order follows the reference.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double psf_model_pixel(const double* __restrict__ pr, int ngauss, double x, double y) {
+    const double x1 = __dsub_rn(__dmul_rn(pr[0], x), __dmul_rn(pr[1], y));
+    const double y1 = __dadd_rn(__dmul_rn(pr[1], x), __dmul_rn(pr[0], y));
+    double rr = __dadd_rn(__dmul_rn(__dmul_rn(pr[2], x1), x1), __dmul_rn(__dmul_rn(pr[3], y1), y1));
+    const double s2 = __dmul_rn(pr[4], pr[4]);
+    double v = 0.0;
+    int ic = 5;
+    for (int ig = 0; ig < ngauss; ++ig) {
+        const double f = exp(rr);
+        double a1 = 1.0;
+        for (int m = 0; m <= 2; ++m) {
+            double a2 = 1.0;
+            for (int n = 0; n <= 2 - m; ++n) {
+                v = __dadd_rn(v, __dmul_rn(__dmul_rn(__dmul_rn(pr[ic], f), a1), a2));
+                ++ic;
+                a2 = __dmul_rn(a2, y);
+            }
+            a1 = __dmul_rn(a1, x);
+        }
+        rr = __dmul_rn(rr, s2);
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void bsgp_psf_model_kernel(const double* __restrict__ params, int stride, int ngauss, int hw, int ny, int nx, int normalize, T* __restrict__ out) {
+    __shared__ double part[32];
+    __shared__ double total;
+    const double* pr = params + (size_t)blockIdx.x * stride;
+    T* o = out + (size_t)blockIdx.x * ny * nx;
+    const int side = 2 * hw + 1, npix = side * side;
+    const int cy = ny / 2, cx = nx / 2;
+    for (int e = threadIdx.x; e < ny * nx; e += blockDim.x) o[e] = (T)0;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < npix; e += blockDim.x) {
+        const int i = e / side - hw, j = e % side - hw;              // i: row offset (y), j: column offset (x)
+        s += psf_model_pixel(pr, ngauss, (double)j, (double)i);
+    }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += part[w];
+        total = t;
+    }
+    __syncthreads();
+    const double scale = normalize ? total : 1.0;
+    for (int e = threadIdx.x; e < npix; e += blockDim.x) {
+        const int i = e / side - hw, j = e % side - hw;
+        const int yy = cy + i, xx = cx + j;
+        if (yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue;
+        o[(size_t)yy * nx + xx] = (T)__ddiv_rn(psf_model_pixel(pr, ngauss, (double)j, (double)i), scale);
+    }
+}
+
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -1070,6 +1134,20 @@ int bsgp_assemble_tiles(const void* tiles_dev, const int* origins_dev, int n, in
     if (rc) return rc;
     if (dtype == BSGP_F64) bsgp_assemble_tiles_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (double*)frame_dev, height, width);
     else bsgp_assemble_tiles_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (float*)frame_dev, height, width);
+    CU(cudaGetLastError());
+    return BSGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PSF model (psf/psf_calculate.py:52-111)
+// ------------------------------------------------------------------------------------------------
+int bsgp_psf_model_eval(const double* params_dev, int n, int ngauss, int hw, int ny, int nx, int normalize, int dtype, void* out_dev, int device, void* stream) {
+    if (!params_dev || !out_dev || n < 1 || ngauss < 1 || ngauss > 8 || hw < 0 || ny < 1 || nx < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "bad dtype");
+    CU(cudaSetDevice(device));
+    const int stride = 5 + 6 * ngauss;
+    if (dtype == BSGP_F64) bsgp_psf_model_kernel<double><<<n, 256, 0, (cudaStream_t)stream>>>(params_dev, stride, ngauss, hw, ny, nx, normalize, (double*)out_dev);
+    else bsgp_psf_model_kernel<float><<<n, 256, 0, (cudaStream_t)stream>>>(params_dev, stride, ngauss, hw, ny, nx, normalize, (float*)out_dev);
     CU(cudaGetLastError());
     return BSGP_OK;
 }

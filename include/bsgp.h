@@ -190,6 +190,13 @@ int bsgp_extract_tiles(const void* frame_dev, int height, int width, int dtype, 
 int bsgp_assemble_tiles(const void* tiles_dev, const int* origins_dev, int n, int tile_h, int tile_w, int dtype, int feather,
                         void* frame_dev, int height, int width, int device, void* stream);
 
+/* DIAPL PSF model (psf/psf_calculate.py:52-111, PSF.calc_psf_pix / get_psf_mat / normalize_psf_mat): n PSFs, each from
+ * a parameter row [cos, sin, ax, ay, sigma_inc, ngauss * 6 coefficients] (device, fp64), evaluated on the
+ * (2 hw + 1)^2 support, optionally normalised to sum 1, and written centred at (ny/2, nx/2) of out[n][ny][nx] (zeros
+ * elsewhere): the placement bsgp_set_psf expects. */
+int bsgp_psf_model_eval(const double* params_dev, int n, int ngauss, int hw, int ny, int nx, int normalize, int dtype,
+                        void* out_dev, int device, void* stream);
+
 int bsgp_device_count(void);
 const char* bsgp_last_error_string(void);
 const char* bsgp_version(void);

@@ -561,3 +561,34 @@ def test_tiling_extract_assemble_and_frame_restoration(bs, fixtures, golden):
         xs = golden[n + "/x_sub"]                                          # x[::8, ::8] of the reference's restored tile
         assert np.abs(out[y0:y0 + 256:8, x0:x0 + 256:8] - xs).max() <= 1e-8 * xs.max()
         assert abs(out[y0:y0 + 256, x0:x0 + 256].sum() - float(golden[n + "/sum_x"])) <= 1e-9 * float(golden[n + "/sum_x"])
+
+
+def test_psf_model_against_reference_image(bs, tmp_path):
+    """the DIAPL PSF model evaluated on the device against (1) the unmodified reference class run on
+    the coefficient file it ships and (2) the 31 x 31 image the reference itself wrote from that file
+    (psf/psfccfbrd210048_1_1_img.fits); tests/golden/make_psf_golden.py."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psf_golden.npz"))
+    txt = tmp_path / "psf.bin.txt"
+    txt.write_text("\n".join(repr(float(v)) for v in g["file_values"]) + "\n")
+    p = bs.psf_model.PSF(str(txt))
+    assert (p.hw, p.ngauss, p.ndeg_local, p.ndeg_spat) == (15, 2, 2, 1) and len(p.coeffs) == 36
+    mat = p.get_psf_mat()
+    assert mat.shape == (31, 31)
+    assert np.abs(mat - g["mat"]).max() <= 1e-14 * np.abs(g["mat"]).max()
+    norm = p.normalize_psf_mat()
+    assert np.abs(norm - g["shipped"]).max() <= 1e-14 * g["shipped"].max()
+    assert abs(norm.sum() - 1.0) <= 1e-15 and np.unravel_index(norm.argmax(), norm.shape) == (15, 15)
+    # placement for the solver: centred at (16, 16) of a 32 x 32 stamp, passes the reference's normalisation check, and a
+    # batch of them feeds a solve without any PSF upload
+    emb = p.embedded((32, 32))
+    e = emb.cpu().numpy()
+    assert np.array_equal(e[1:32, 1:32], norm) and e[0].sum() == 0 and e[:, 0].sum() == 0
+    st = bs.synth.star_stamps(4, 32, seed=11)
+    psfs = bs.psf_model.evaluate_batch(np.tile(p.params(), (4, 1)), p.ngauss, p.hw, (32, 32))
+    a = bs.solve_batch(torch.as_tensor(st["gn"], device="cuda:0"), psfs, torch.as_tensor(st["bkg"], device="cuda:0"), divergence="beta",
+                       flux=st["flux"], betaParam=st["beta0"], **bs.synth.STAMP_KWARGS)
+    b = bs.solve_batch(st["gn"], np.tile(e, (4, 1, 1)), st["bkg"], divergence="beta", flux=st["flux"], betaParam=st["beta0"], **bs.synth.STAMP_KWARGS)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.x.cpu().numpy(), b.x) and np.array_equal(a.iters.cpu().numpy(), b.iters)

@@ -251,3 +251,17 @@ def test_tile_boxes_match_reference_golden():
     assert [tuple(o) for o in org.tolist()] == bs.synth.tile_boxes(2048, 2048, 256, 0)
     with pytest.raises(bs._capi.BsgpError):
         bs.tiles.calculate_slice_bboxes(100, 100, 10, 10, 1.0, 0.0)          # the reference would loop forever
+
+
+def test_psf_model_file_parsing(tmp_path):
+    """PSF(txt_file) reads a DIAPL coefficient file like psf_calculate.py:8-46 (host only; the evaluation is a CUDA kernel)."""
+    import beta_sgp_b200 as bs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psf_golden.npz"))
+    txt = tmp_path / "psf.bin.txt"
+    txt.write_text("\n".join(repr(float(v)) for v in g["file_values"]) + "\n")
+    p = bs.psf_model.PSF(str(txt))
+    assert (p.hw, p.ndeg_spat, p.ndeg_local, p.ngauss) == (15, 1, 2, 2)
+    assert (p.cos, p.sin, p.ax, p.ay, p.sigma_inc) == tuple(g["file_values"][[5, 6, 7, 8, 9]])
+    assert p.ntot == 36 and len(p.coeffs) == 36
+    row = p.params()
+    assert row.shape == (5 + 12,) and np.array_equal(row[5:], g["file_values"][14:26])
