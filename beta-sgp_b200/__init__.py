@@ -5,7 +5,8 @@ restoration/flux_conserve_proj.py) plus batched variants.  The directory name ca
 layout); import it as ``beta_sgp_b200`` (alias package at the repo root) or put this directory on
 ``sys.path`` and ``from sgp import sgp, sgp_betaDiv`` like the reference's scripts do.
 """
-from . import _capi, engine, psf_model, shard, synth, tiles  # noqa: F401
+from . import _capi, engine, psf_model, shard, sweep, synth, tiles  # noqa: F401
+from .sweep import sgp_betaDiv_sweep  # noqa: F401
 from .engine import BatchResult, Plan, clear_plans, get_plan, project_batch, solve_batch  # noqa: F401
 from .flux_conserve_proj import projectDF  # noqa: F401
 from .shard import solve_batch_sharded  # noqa: F401
@@ -25,4 +26,4 @@ def sgp_betaDiv_batch(gn, psf, bkg, **kw):
 
 __all__ = ["sgp", "sgp_betaDiv", "projectDF", "sgp_batch", "sgp_betaDiv_batch", "solve_batch", "solve_batch_sharded", "project_batch", "Plan",
            "get_plan", "clear_plans", "BatchResult", "PsfOperator", "betaDiv", "betaDivDeriv", "betaDivDerivwrtY",
-           "lr_schedule", "DEFAULT_PARAMS", "DEFAULT_COLUMNS", "synth", "tiles", "psf_model"]
+           "lr_schedule", "DEFAULT_PARAMS", "DEFAULT_COLUMNS", "synth", "tiles", "psf_model", "sweep", "sgp_betaDiv_sweep"]

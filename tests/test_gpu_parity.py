@@ -592,3 +592,43 @@ def test_psf_model_against_reference_image(bs, tmp_path):
     b = bs.solve_batch(st["gn"], np.tile(e, (4, 1, 1)), st["bkg"], divergence="beta", flux=st["flux"], betaParam=st["beta0"], **bs.synth.STAMP_KWARGS)
     torch.cuda.synchronize()
     assert np.array_equal(a.x.cpu().numpy(), b.x) and np.array_equal(a.iters.cpu().numpy(), b.iters)
+
+
+def test_beta_sweep_selection(bs, fixtures, golden):
+    """the five-beta sweep of application_sgp_star_stamps.py:69-105 as one launch.  Every (stamp, beta)
+    entry equals its single solve; the selection follows the reference's rule (signed flux_fractional_difference, first
+    strict minimum); the selected run is bit-identical to the reference's sixth re-run, which is therefore not needed."""
+    import torch
+    S = 6
+    gn = np.stack([fixtures[f"stamp{i}/gn"] for i in range(S)])
+    psf = np.stack([fixtures[f"stamp{i}/psf"] for i in range(S)])
+    bkg = np.array([float(fixtures[f"stamp{i}/bkg"]) for i in range(S)])
+    flux = np.array([float(golden[f"stamp{i:02d}/flux_in"]) for i in range(S)])
+    betas = np.array(bs.synth.beta_inits())
+    assert np.allclose(betas, [1.0882026, 1.0248357, 0.9703266, 1.0815099, 1.0064847], atol=5e-8)     # seeds 0, 42, 951, 93, 810
+    best, best_beta, best_idx, metric, sweep = bs.sgp_betaDiv_sweep(gn, psf, bkg, flux=flux, **bs.synth.STAMP_KWARGS)
+    torch.cuda.synchronize()
+    assert metric.shape == (S, 5) and tuple(sweep.x.shape) == (S * 5, 32, 32)
+    xs, its = sweep.x.cpu().numpy(), sweep.iters.cpu().numpy()
+    for s in range(S):
+        for k in range(5):
+            one = bs.solve_batch(gn[s:s + 1], psf[s], bkg[s:s + 1], divergence="beta", flux=flux[s:s + 1], betaParam=float(betas[k]), **bs.synth.STAMP_KWARGS)
+            assert np.array_equal(one.x[0], xs[s * 5 + k]) and int(one.iters[0]) == int(its[s * 5 + k])
+        # golden stamp i was generated with beta index i % 5 (application shape): the sweep contains the reference's run
+        k = s % 5
+        assert abs(betas[k] - float(golden[f"stamp{s:02d}/beta0"])) < 1e-15
+        assert int(its[s * 5 + k]) == int(golden[f"stamp{s:02d}/iters"])
+        assert np.abs(xs[s * 5 + k] - golden[f"stamp{s:02d}/x"]).max() <= 1e-8 * golden[f"stamp{s:02d}/x"].max()
+    # selection rule restated
+    for s in range(S):
+        cur, pick = np.inf, None
+        for k in range(5):
+            if metric[s, k] < cur:
+                cur, pick = metric[s, k], k
+        assert pick == best_idx[s] and best_beta[s] == betas[pick]
+        rerun = bs.solve_batch(gn[s:s + 1], psf[s], bkg[s:s + 1], divergence="beta", flux=flux[s:s + 1], betaParam=float(best_beta[s]), **bs.synth.STAMP_KWARGS)
+        assert np.array_equal(rerun.x[0], best.x[s].cpu().numpy()) and int(rerun.iters[0]) == int(best.iters[s])
+    # the stand-in measurement: aperture sum around the peak, background removed
+    img = torch.zeros(1, 32, 32, dtype=torch.float64, device="cuda:0") + 3.0
+    img[0, 10, 20] += 100.0; img[0, 12, 21] += 50.0; img[0, 30, 2] += 7.0
+    assert abs(float(bs.sweep.aperture_flux(img, torch.tensor([3.0], device="cuda:0"))[0]) - 150.0) < 1e-12
