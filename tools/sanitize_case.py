@@ -19,3 +19,13 @@ t = bs.synth.field_tiles(size=512, tile=256, seed=1, n_beta=2, max_tiles=1)
 kw = dict(bs.synth.TILE_KWARGS, MAXIT=3)
 r = bs.sgp_betaDiv_batch(t["gn"], t["psf"], t["bkg"], flux=t["flux"], betaParam=t["beta0"], **kw)
 print("tiles", r.iters, r.status)
+# pipelined host path (ready flags, zero-copy output), tiling kernels, PSF model
+import torch
+r2 = bs.sgp_betaDiv_batch(torch.as_tensor(t["gn"]).pin_memory(), t["psf"], torch.as_tensor(t["bkg"]).pin_memory(), flux=t["flux"], betaParam=t["beta0"], **kw)
+print("tiles, pinned path", r2.iters, r2.status, bool(np.array_equal(r2.x.numpy(), r.x)))
+frame = np.random.default_rng(2).random((300, 200))
+tl, org = bs.tiles.create_subdivisions(frame, (128, 64), 9)
+back = bs.tiles.reconstruct_full_image_from_patches(tl, org, frame.shape)
+print("tiling", tuple(tl.shape), float((back.cpu() - torch.as_tensor(frame)).abs().max()))
+pm = bs.psf_model.evaluate_batch(np.array([[0.0084, 0.99996, -0.1267, -0.1662, 0.548] + [0.1] + [0.0] * 11]), 2, 15, (32, 32))
+print("psf model", float(pm.sum()))
