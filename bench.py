@@ -86,7 +86,33 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
+    def _nvml_loop(self):
+        import pynvml as nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.nvml_rows.append((float(sm), [n for n, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
     def start(self):
+        # NVML in-process (a sample every 20 ms: a 5-step timed region of 0.4 s gets ~20); nvidia-smi -lms as the fallback
+        self.nvml_rows, self.h = [], None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -100,6 +126,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if getattr(self, "h", None) is not None:
+            self.stop_flag.set()
+            self.t.join(1.0)
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted({n for r in self.nvml_rows for n in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
