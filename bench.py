@@ -379,7 +379,7 @@ def main():
                        "cluster_slot_utilisation": slot_util},
             "ms_per_image_iteration": ms * 1e-3 * 1e3 / (total_iters * args.steps) if total_iters else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "bsgp_solve_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
+                         "kernel": "bsgp_frame_kernel" if info["cluster_size"] > 16 else "bsgp_solve_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": abytes,
                          "peak_source": peak_src},
             "e2e": {"value": images / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 2 * args.steps,
