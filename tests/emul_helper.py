@@ -29,7 +29,10 @@ def build(force=False):
     deps.append(os.path.join(ROOT, "include", "bsgp.h"))
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, SRC])
+    # inline functions and their local statics stay private to this library: the product library (loaded by other tests in
+    # the same process) defines the same bsgp:: inline symbols, possibly from an older build
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility-inlines-hidden",
+                           "-fno-gnu-unique", "-Wl,-Bsymbolic", "-o", SO, SRC])
     return SO
 
 
