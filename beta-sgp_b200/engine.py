@@ -198,18 +198,27 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
     506-513).  numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (asynchronous on the
     current stream); PINNED CPU tensors in -> pinned CPU tensors out through the pipelined host path
     (upload, solve and download overlap; see bsgp_solve_batch_pinned in include/bsgp.h; ``x_out`` may name a
-    pinned tensor that receives the restored images, so that a caller in a loop reuses its buffer).  ``padded=True`` selects the zero-padded operator of use_original_SGP_Afunction=False
-    (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size."""
+    pinned tensor that receives the restored images, so that a caller in a loop reuses its buffer); pageable CPU tensors
+    are treated like numpy arrays.  ``padded=True`` selects the zero-padded operator of
+    use_original_SGP_Afunction=False (sgp.py:121-161): images of any size, kernel of any (smaller or equal) size."""
     if divergence not in ("kl", "beta"):
         raise ValueError("divergence must be 'kl' or 'beta'")
+    if padded:
+        if _is_tensor(gn) and not gn.is_cuda:             # CPU tensors (pinned or not) take the numpy route of the padded operator
+            def host(a):
+                return a.numpy() if _is_tensor(a) and not a.is_cuda else a
+            gn, psf, bkg, flux, betaParam, x0, obj = (host(a) for a in (gn, psf, bkg, flux, betaParam, x0, obj))
+            x_out = None
+        return _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw)
     if x_out is not None and not (_is_tensor(gn) and not gn.is_cuda and gn.is_pinned()):
         raise ValueError("x_out is only supported with pinned CPU tensor inputs")
-    if padded:
-        return _solve_batch_padded(gn, psf, bkg, divergence, flux, betaParam, x0, obj, dtype, device, trace, kw)
     if _is_tensor(gn) and not gn.is_cuda and gn.is_pinned():
         return _solve_batch_pinned(gn, psf, bkg, divergence, flux, betaParam, x0, obj, device, trace, plan, psf_is_set, x_out, kw)
-    if _is_tensor(gn):
+    if _is_tensor(gn) and gn.is_cuda:
         return _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trace, plan, psf_is_set, kw)
+    if _is_tensor(gn):                                    # pageable CPU tensor: the plain host path
+        gn = gn.numpy()
+        psf, bkg, flux, betaParam, x0, obj = (a.numpy() if _is_tensor(a) and not a.is_cuda else a for a in (psf, bkg, flux, betaParam, x0, obj))
     npdt = _NP[dtype]
     gn = np.ascontiguousarray(gn, dtype=npdt)
     if gn.ndim != 3:

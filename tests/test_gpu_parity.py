@@ -508,6 +508,14 @@ def test_pipelined_pinned_path_matches_numpy_path(bs, fixtures, golden):
     assert np.array_equal(p.x.numpy(), a.x) and np.array_equal(p.discr, a.discr)
     with pytest.raises(ValueError):
         bs.solve_batch(torch.as_tensor(gg).pin_memory(), psf1, bkg1, divergence="kl", x0=torch.as_tensor(x0), **kw)
+    # pageable CPU tensors are treated like numpy arrays; the zero-padded operator accepts CPU tensors as well
+    q = bs.solve_batch(torch.as_tensor(gg), torch.as_tensor(psf1), bkg1, divergence="kl", x0=torch.as_tensor(x0), **kw)
+    assert isinstance(q.x, np.ndarray) and np.array_equal(q.x, a.x)
+    small = np.ascontiguousarray(g1[:31, :31])[None]
+    k7 = bs.synth.moffat_psf(7, 7, 2.0)
+    pa = bs.solve_batch(small, k7, np.array([float(bkg1)]), divergence="kl", padded=True, init_recon=3, stop_criterion=1, MAXIT=4)
+    pb = bs.solve_batch(torch.as_tensor(small).pin_memory(), k7, np.array([float(bkg1)]), divergence="kl", padded=True, init_recon=3, stop_criterion=1, MAXIT=4)
+    assert np.array_equal(pa.x, pb.x)
 
 
 def test_tiling_extract_assemble_and_frame_restoration(bs, fixtures, golden):
