@@ -54,7 +54,7 @@ class Outputs(C.Structure):
 class PlanInfo(C.Structure):
     _fields_ = [("ny", C.c_int), ("nx", C.c_int), ("dtype", C.c_int), ("device", C.c_int), ("cluster_size", C.c_int),
                 ("num_clusters", C.c_int), ("threads", C.c_int), ("smem_bytes", C.c_int), ("num_sms", C.c_int),
-                ("resident_mask", C.c_int), ("workspace_bytes", C.c_longlong)]
+                ("resident_mask", C.c_int), ("workspace_bytes", C.c_longlong), ("grid_ny", C.c_int), ("grid_nx", C.c_int)]
 
 
 def make_params(divergence, *, init_recon=0, proj_type=0, stop_criterion=0, MAXIT=500, gamma=1e-4, beta=0.4, alpha=1.3,
@@ -109,8 +109,8 @@ def lib():
         L.bsgp_solve_batch_pinned.argtypes = [vp, C.POINTER(Params), ip, C.POINTER(Inputs), C.POINTER(Outputs), vp]
     L.bsgp_apply_psf.argtypes = [vp, vp, vp, ip, ip, vp]
     L.bsgp_apply_psf_host.argtypes = [vp, vp, vp, ip, ip]
-    L.bsgp_project_df.argtypes = [vp, vp, vp, ip, ip, dp, dp, dp, dp, ip, vp, vp, vp, ip, vp]
-    L.bsgp_project_df_host.argtypes = [vp, vp, vp, ip, ip, dp, dp, dp, dp, ip, vp, vp, vp, ip]
+    L.bsgp_project_df.argtypes = [vp, vp, vp, ip, ip, dp, dp, dp, dp, ip, ip, ip, vp, vp, vp, ip, vp]
+    L.bsgp_project_df_host.argtypes = [vp, vp, vp, ip, ip, dp, dp, dp, dp, ip, ip, ip, vp, vp, vp, ip]
     L.bsgp_beta_div_host.argtypes = [vp, vp, C.c_longlong, dp, vp, vp, ip]
     L.bsgp_beta_grad_terms_host.argtypes = [vp, vp, C.c_longlong, dp, vp, vp, ip]
     if hasattr(L, "bsgp_tile_boxes"):

@@ -45,6 +45,10 @@ struct ConvGeom {
     int lg_cp;               // log2 of the panel width of the exchange buffer: cols_per_cta (narrow column tiles) or hx (row-major)
     int rowstride;           // padded complex elements per row pair in the workspace
     int colstride;           // padded complex elements per column in the workspace (odd)
+    // Arbitrary-size circular operator (bsgp_kernels.cu, "wrapped plans"): the ny x nx grid holds an image of
+    // wrap_ny x wrap_nx pixels at its origin, zero elsewhere, and the kernel's linear convolution with it; the circular
+    // result is obtained by folding: out[i] = z[i] + z[i + wrap_n] along each wrapped axis (0 = axis not wrapped).
+    int wrap_ny, wrap_nx;
     FftPlan px, py;
 };
 
@@ -52,11 +56,11 @@ enum ConvMode { CONV_TF = 0, CONV_CTF = 1, CONV_MAKE_TF = 2 };
 
 // the scalars of ConvGeom the row passes need, copied to registers once per pass (the geometry itself
 // lives in shared memory, where every store through another pointer would force a reload)
-struct RowGeom { int nx, hx, lg_nx, lg_hx, lg_ny, lg_cp, rows_per_cta, row_tile_pairs, rowstride, ps; };
+struct RowGeom { int nx, hx, lg_nx, lg_hx, lg_ny, lg_cp, rows_per_cta, row_tile_pairs, rowstride, ps, wrap_nx; };
 BSGP_DEV RowGeom row_geom(const ConvGeom& g) {
     RowGeom r;
     r.nx = g.nx; r.hx = g.hx; r.lg_nx = g.lg_nx; r.lg_hx = g.lg_hx; r.lg_ny = g.lg_ny; r.lg_cp = g.lg_cp; r.rows_per_cta = g.rows_per_cta;
-    r.row_tile_pairs = g.row_tile_pairs; r.rowstride = g.rowstride; r.ps = g.px.pad_shift;
+    r.row_tile_pairs = g.row_tile_pairs; r.rowstride = g.rowstride; r.ps = g.px.pad_shift; r.wrap_nx = g.wrap_nx;
     return r;
 }
 
@@ -267,6 +271,15 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
         ctx.sync();
         if (Ctx::kFrame && tw_split) fft_batch_split<true, Ctx, T>(ctx, ws_off, ct, g.colstride, py, twy_off);
         else fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
+        if (gp->wrap_ny > 0) {                            // wrapped plan: fold the linear result along the rows, z[i] += z[i + n]
+            const int wn = gp->wrap_ny;
+            for (int e = ctx.tid; e < ct * wn; e += ctx.nt) {
+                const int cl = e / wn, row = e - cl * wn;
+                cplx<T>* col = ws + cl * g.colstride;
+                col[fpad(row, ps)] = cadd(col[fpad(row, ps)], col[fpad(row + wn, ps)]);
+            }
+            ctx.sync();
+        }
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int row = e >> g.lg_col_tile, cl = e & (ct - 1);
             spec[spec_idx<Ctx::kFrame>(row, cc0 + cl, g.lg_ny, g.lg_cp, g.hx)] = ws[cl * g.colstride + fpad(row, ps)];
@@ -276,7 +289,8 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 }
 
 // Consumer: In fetch(i); void apply(i, In, V2 value) for the slab pixel pair (i, i + 1).
-template <int U, class Ctx, typename T, class Fetch, class Apply>
+// WRAP: the geometry may ask for the column fold of a wrapped plan (value(c) = z[c] + z[c + wrap_nx] for c < wrap_nx).
+template <int U, bool WRAP = false, class Ctx, typename T, class Fetch, class Apply>
 BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
@@ -339,7 +353,8 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                     const int p = e >> g.lg_hx, c = 2 * (e & (g.hx - 1));
                     const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
                     const cplx<T>* row = ws + p * g.rowstride;
-                    const cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                    cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                    if (WRAP && c < g.wrap_nx) { z0 = cadd(z0, row[fpad(c + g.wrap_nx, ps)]); z1 = cadd(z1, row[fpad(c + 1 + g.wrap_nx, ps)]); }
                     apply(i0, in0[u], mk2<T>(z0.re, z1.re));
                     apply(i0 + g.nx, in1[u], mk2<T>(z0.im, z1.im));
                 }
@@ -350,7 +365,8 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 const auto a0 = fetch(i0);
                 const auto a1 = fetch(i0 + g.nx);
                 const cplx<T>* row = ws + p * g.rowstride;
-                const cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                cplx<T> z0 = row[fpad(c, ps)], z1 = row[fpad(c + 1, ps)];
+                if (WRAP && c < g.wrap_nx) { z0 = cadd(z0, row[fpad(c + g.wrap_nx, ps)]); z1 = cadd(z1, row[fpad(c + 1 + g.wrap_nx, ps)]); }
                 apply(i0, a0, mk2<T>(z0.re, z1.re));
                 apply(i0 + g.nx, a1, mk2<T>(z0.im, z1.im));
             }

@@ -28,6 +28,7 @@
 #include "bsgp_launch.h"
 #include "bsgp_plan.h"
 #include "bsgp_solver.cuh"
+#include "bsgp_wrap.h"
 
 using namespace bsgp;
 
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             ctx.cluster_sync();
             conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
-            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, cf, ca);
+            conv_rows_inverse<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
             ctx.cluster_sync();
             conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
-            conv_rows_inverse<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, cf, ca);
+            conv_rows_inverse<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, cf, ca);
         }
         ctx.cluster_sync();   // spec is reused by the next item
     }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
 // projectDF (flux_conserve_proj.py:7-144): one CTA per problem, x = clamp((c + lambda) / dia).
 __global__ void __launch_bounds__(512, 1) bsgp_project_kernel(const double* __restrict__ b, const double* __restrict__ c,
                                                               const double* __restrict__ dia, int n, int batch, double cap, int has_cap,
-                                                              double lambda0, double dlambda0, double tol_lam, int max_projs,
+                                                              double lambda0, double dlambda0, double tol_lam, int max_projs, int biter0, int siter0,
                                                               double* __restrict__ x, int* evals, int* status) {
     __shared__ SharedCtl ctl;
     DeviceCtx ctx = make_ctx(&ctl, 1);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(512, 1) bsgp_project_kernel(const double* __re
             ctx.allreduce_sum(&t, 1);
             return t - target;
         };
-        const ProjResult pr = flux_rootfind(eval, target, max_projs, lambda0, dlambda0, tol_lam);
+        const ProjResult pr = flux_rootfind(eval, target, max_projs, lambda0, dlambda0, tol_lam, biter0, siter0);
         for (int i = ctx.tid; i < n; i += ctx.nt) x[(size_t)p * n + i] = point(i, pr.lambda);
         if (ctx.tid == 0) { if (evals) evals[p] = pr.evals; if (status) status[p] = pr.status; }
         __syncthreads();
@@ -237,6 +238,49 @@ __global__ void bsgp_assemble_tiles_kernel(const T* __restrict__ tiles, const in
             den += w;
         }
         frame[e] = den > 0.0 ? (T)(num / den) : (T)0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wrapped plans: image sides that are not a power of two in [16, 8192] (the reference's numpy closure takes any
+// size, sgp.py:108-120; its star-stamp application runs it on 31 x 31 cut-outs, application_sgp_star_stamps.py:24,58).
+// The image sits at the origin of a power-of-two grid of side P >= 2 n - 1 (zeros elsewhere) and the circular
+// convolution with h = fftshift(psf) (sgp.py:109: np.roll by n // 2, which for odd n puts the PSF centre at index
+// n - 1, not 0) is computed as the LINEAR convolution on the grid followed by the fold out[i] = z[i] + z[i + n]
+// (conv_cols / conv_rows_inverse).  A^T = correlation with h = convolution with h~[j] = h[(-j) mod n], so both
+// operators are "kernel on [0, n)^2, CONV_TF, fold"; the plan keeps the two spectra (tf, tf_adj).
+// The kernels below move user arrays [count][iny][inx] to / from the grid [count][ny][nx]; pure data movement,
+// one pixel per thread, consecutive threads consecutive columns, grids sized in multiples of the SM count.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bsgp_embed_images_kernel(const T* __restrict__ src, int iny, int inx, T* __restrict__ dst, int ny, int nx, size_t count) {
+    const size_t per = (size_t)ny * nx, total = per * count;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / per;
+        const int r = (int)((e - b * per) / nx), c = (int)(e - b * per - (size_t)r * nx);
+        dst[e] = (r < iny && c < inx) ? src[(b * iny + r) * inx + c] : (T)0;
+    }
+}
+
+template <typename T>
+__global__ void bsgp_crop_images_kernel(const T* __restrict__ src, int ny, int nx, T* __restrict__ dst, int iny, int inx, size_t count) {
+    const size_t per = (size_t)iny * inx, total = per * count;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / per;
+        const int r = (int)((e - b * per) / inx), c = (int)(e - b * per - (size_t)r * inx);
+        dst[e] = src[(b * ny + r) * nx + c];
+    }
+}
+
+// the kernel of A (adjoint = 0) or A^T (adjoint = 1) on the grid, in the placement CONV_MAKE_TF expects (bsgp_wrap.h)
+template <typename T>
+__global__ void bsgp_embed_psf_kernel(const T* __restrict__ psf, int iny, int inx, T* __restrict__ out, int ny, int nx, size_t count, int adjoint) {
+    const size_t per = (size_t)ny * nx, total = per * count;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / per;
+        const int r = (int)((e - b * per) / nx), c = (int)(e - b * per - (size_t)r * nx);
+        int sr, sc;
+        out[e] = wrap_psf_source(r, c, ny, nx, iny, inx, adjoint, &sr, &sc) ? psf[(b * iny + sr) * inx + sc] : (T)0;
     }
 }
 
@@ -324,7 +368,12 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 struct bsgp_plan {
-    int ny = 0, nx = 0, dtype = 0, device = 0;
+    int ny = 0, nx = 0, dtype = 0, device = 0;   // ny, nx: the power-of-two FFT grid the kernels work on
+    int img_ny = 0, img_nx = 0;                   // the caller's image shape (== grid unless the plan is wrapped)
+    bool embedded = false;                        // wrapped plan: user arrays are moved to / from the grid by the library
+    void* emb_psf = nullptr; size_t emb_psf_cap = 0;   // grow-only staging: PSFs on the grid
+    void* emb_img = nullptr; size_t emb_img_cap = 0;   //                    images on the grid (inputs and restored output)
+    cudaEvent_t ev_last = nullptr;                // completion of the plan's most recent launch (cross-stream ordering)
     int num_sms = 0, max_smem = 0, smem_per_sm = 0;
     int want_G = 0, want_threads = 0;
     bool configured = false;
@@ -353,6 +402,9 @@ template <typename T> static const void* conv_kernel_ptr() { return (const void*
 
 static void plan_free_pipeline(bsgp_plan* p) {
     cudaFree(p->stage); cudaFree(p->ready); cudaFreeHost(p->ones_host);
+    cudaFree(p->emb_psf); cudaFree(p->emb_img);
+    p->emb_psf = p->emb_img = nullptr; p->emb_psf_cap = p->emb_img_cap = 0;
+    if (p->ev_last) { cudaEventDestroy(p->ev_last); p->ev_last = nullptr; }
     p->stage = nullptr; p->stage_cap = 0; p->ready = nullptr; p->ones_host = nullptr; p->ready_cap = 0;
     if (p->s_copy) cudaStreamDestroy(p->s_copy);
     if (p->s_run) cudaStreamDestroy(p->s_run);
@@ -541,7 +593,57 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
 static int plan_setup(bsgp_plan* p) {
     if (p->configured) return BSGP_OK;
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? plan_setup_t<double>(p) : plan_setup_t<float>(p);
+    const int rc = p->dtype == BSGP_F64 ? plan_setup_t<double>(p) : plan_setup_t<float>(p);
+    if (rc) return rc;
+    p->g.wrap_ny = p->ny != p->img_ny ? p->img_ny : 0;
+    p->g.wrap_nx = p->nx != p->img_nx ? p->img_nx : 0;
+    return BSGP_OK;
+}
+
+// Stream ordering of a plan.  A plan owns mutable device state (PSF spectra, per-cluster scratch, the work-queue counter),
+// so two launches on the same plan must not overlap.  Every public device entry point makes its stream wait for the
+// plan's previous launch and records its own completion: callers may use one plan from several streams, the launches
+// are serialised on the device (include/bsgp.h, "Streams").
+static int plan_enter(bsgp_plan* p, cudaStream_t st) {
+    if (!p->ev_last) { CU(cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming)); return BSGP_OK; }
+    CU(cudaStreamWaitEvent(st, p->ev_last, 0));
+    return BSGP_OK;
+}
+static int plan_leave(bsgp_plan* p, cudaStream_t st) {
+    CU(cudaEventRecord(p->ev_last, st));
+    return BSGP_OK;
+}
+
+static int grow(void** buf, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return BSGP_OK;
+    cudaFree(*buf); *buf = nullptr; *cap = 0;           // cudaFree waits for the work that may still use the old buffer
+    CU(cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return BSGP_OK;
+}
+
+static int data_grid(int device, size_t total, int* blocks) {
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    size_t want = (total + 255) / 256, cap = (size_t)sms * 8;          // 8 CTAs of 256 threads per SM, grid-stride beyond
+    *blocks = (int)(want < cap ? (want ? want : 1) : cap);
+    return BSGP_OK;
+}
+
+// user images [count][img_ny][img_nx] -> grid [count][ny][nx] (zeros in the padding) and back
+template <typename T> static int embed_images(bsgp_plan* p, const void* src, void* dst, size_t count, cudaStream_t st) {
+    int blocks = 0, rc = data_grid(p->device, count * p->ny * p->nx, &blocks);
+    if (rc) return rc;
+    bsgp_embed_images_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, p->img_ny, p->img_nx, (T*)dst, p->ny, p->nx, count);
+    CU(cudaGetLastError());
+    return BSGP_OK;
+}
+template <typename T> static int crop_images(bsgp_plan* p, const void* src, void* dst, size_t count, cudaStream_t st) {
+    int blocks = 0, rc = data_grid(p->device, count * p->img_ny * p->img_nx, &blocks);
+    if (rc) return rc;
+    bsgp_crop_images_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, p->ny, p->nx, (T*)dst, p->img_ny, p->img_nx, count);
+    CU(cudaGetLastError());
+    return BSGP_OK;
 }
 
 template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int count, cudaStream_t st) {
@@ -586,11 +688,76 @@ template <typename T> static int apply_psf_t(bsgp_plan* p, const void* x, void* 
     a.g = p->g; a.count = batch; a.in = (const T*)x; a.out = (T*)y;
     a.twx = (const cplx<T>*)p->twx; a.twy = (const cplx<T>*)p->twy; a.tf = (cplx<T>*)p->tf; a.n_psf = p->n_psf; a.tf_stride = p->tf_stride;
     a.spec = (cplx<T>*)p->spec; a.spec_stride = p->spec_stride; a.mode = adjoint ? CONV_CTF : CONV_TF; a.queue = p->queue;
-    return launch_conv<T>(p, a, batch, st);
+    if (!p->embedded) return launch_conv<T>(p, a, batch, st);
+    // wrapped plan: embed, convolve on the grid with the spectrum of h (A) or of h~ (A^T), fold (in the kernel), crop
+    const size_t gb = (size_t)batch * p->ny * p->nx * sizeof(T);
+    int rc = grow(&p->emb_img, &p->emb_img_cap, 2 * gb);
+    if (rc) return rc;
+    T* xe = (T*)p->emb_img; T* ye = (T*)((char*)p->emb_img + gb);
+    rc = embed_images<T>(p, x, xe, batch, st);
+    if (rc) return rc;
+    a.in = xe; a.out = ye; a.mode = CONV_TF;
+    if (adjoint) a.tf = (cplx<T>*)p->tf_adj;
+    rc = launch_conv<T>(p, a, batch, st);
+    if (rc) return rc;
+    return crop_images<T>(p, ye, y, batch, st);
+}
+
+// bsgp_set_psf on a wrapped plan: both kernels (h for A, h~ for A^T) are built on the grid from the caller's PSFs
+template <typename T> static int set_psf_wrapped(bsgp_plan* p, const void* psf_dev, int n_psf, cudaStream_t st) {
+    const size_t gb = (size_t)n_psf * p->ny * p->nx * sizeof(T);
+    int rc = grow(&p->emb_psf, &p->emb_psf_cap, gb);
+    if (rc) return rc;
+    int blocks = 0;
+    rc = data_grid(p->device, (size_t)n_psf * p->ny * p->nx, &blocks);
+    if (rc) return rc;
+    for (int adj = 0; adj < 2; ++adj) {
+        bsgp_embed_psf_kernel<T><<<blocks, 256, 0, st>>>((const T*)psf_dev, p->img_ny, p->img_nx, (T*)p->emb_psf, p->ny, p->nx, (size_t)n_psf, adj);
+        CU(cudaGetLastError());
+        rc = set_psf_t<T>(p, p->emb_psf, n_psf, st, adj != 0);
+        if (rc) return rc;
+    }
+    return BSGP_OK;
 }
 
 template <typename T>
+static int solve_grid(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, cudaStream_t st, const int* ready);
+
+// wrapped plans: move the caller's arrays onto the grid, solve there with the image window as the valid region (the
+// zero-padded operator's masked kernels) and the fold of the geometry, crop the restored images
+template <typename T>
 static int solve_t(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, cudaStream_t st, const int* ready) {
+    if (!p->embedded) return solve_grid<T>(p, prm, batch, in, out, st, ready);
+    const size_t gb = (size_t)batch * p->ny * p->nx * sizeof(T);
+    const int narr = 2 + (in->bkg_is_image ? 1 : 0) + (in->x0 ? 1 : 0) + (in->obj ? 1 : 0);
+    int rc = grow(&p->emb_img, &p->emb_img_cap, (size_t)narr * gb);
+    if (rc) return rc;
+    char* base = (char*)p->emb_img;
+    int k = 0;
+    auto up = [&](const void* src, const void** dst) -> int {
+        if (!src) { *dst = nullptr; return BSGP_OK; }
+        void* d = base + (size_t)(k++) * gb;
+        *dst = d;
+        return embed_images<T>(p, src, d, (size_t)batch, st);
+    };
+    bsgp_inputs gi = *in;
+    bsgp_outputs go = *out;
+    if ((rc = up(in->gn, &gi.gn))) return rc;
+    if (in->bkg_is_image && (rc = up(in->bkg, &gi.bkg))) return rc;
+    if ((rc = up(in->x0, &gi.x0))) return rc;
+    if ((rc = up(in->obj, &gi.obj))) return rc;
+    go.x = base + (size_t)(k++) * gb;
+    bsgp_params q = *prm;
+    q.region[0] = 0; q.region[1] = p->img_ny; q.region[2] = 0; q.region[3] = p->img_nx;
+    q.div_a = q.div_at = 1.0;
+    q.adjoint_second_psf = 1;
+    rc = solve_grid<T>(p, &q, batch, &gi, &go, st, ready);
+    if (rc) return rc;
+    return crop_images<T>(p, go.x, out->x, (size_t)batch, st);
+}
+
+template <typename T>
+static int solve_grid(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, cudaStream_t st, const int* ready) {
     SolveArgs<T> a;
     memset(&a, 0, sizeof a);
     a.p = *prm; a.g = p->g; a.batch = batch;
@@ -642,14 +809,21 @@ int bsgp_device_count(void) {
     return n;
 }
 const char* bsgp_last_error_string(void) { return g_err.c_str(); }
-const char* bsgp_version(void) { return "libbsgp 0.1 (sm_100a)"; }
+#ifndef BSGP_SRC_HASH
+#define BSGP_SRC_HASH "unknown"
+#endif
+const char* bsgp_version(void) { return "libbsgp 0.2 (sm_100a) src:" BSGP_SRC_HASH; }
 
 int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan) {
     if (!plan) return fail(BSGP_E_ARG, "plan is NULL");
     *plan = nullptr;
     if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "dtype must be BSGP_F64 or BSGP_F32");
-    if (!is_pow2(ny) || !is_pow2(nx) || ny < 16 || nx < 16 || ny > 8192 || nx > 8192)
-        return fail(BSGP_E_SHAPE, "unsupported image shape %dx%d: the cluster solver handles power-of-two sides in [16, 8192]", ny, nx);
+    if (ny < 1 || nx < 1) return fail(BSGP_E_SHAPE, "unsupported image shape %dx%d", ny, nx);
+    // FFT grid: a power-of-two side in [16, 8192] is used as it is; any other side n runs on a grid of side
+    // P = 2^k >= 2 n - 1 (linear convolution + fold, see "Wrapped plans" above)
+    const int gy = wrap_grid_side(ny), gx = wrap_grid_side(nx);
+    if (gy > 8192 || gx > 8192)
+        return fail(BSGP_E_SHAPE, "unsupported image shape %dx%d: sides that are not a power of two are limited to 4096 (FFT grid of 8192)", ny, nx);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(BSGP_E_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
@@ -658,7 +832,8 @@ int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 9) return fail(BSGP_E_CUDA, "thread-block clusters need compute capability >= 9.0 (found %d.%d)", prop.major, prop.minor);
     bsgp_plan* p = new bsgp_plan();
-    p->ny = ny; p->nx = nx; p->dtype = dtype; p->device = device;
+    p->ny = gy; p->nx = gx; p->img_ny = ny; p->img_nx = nx; p->embedded = (gy != ny || gx != nx);
+    p->dtype = dtype; p->device = device;
     p->num_sms = prop.multiProcessorCount;
     p->max_smem = (int)prop.sharedMemPerBlockOptin;
     p->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
@@ -690,7 +865,8 @@ int bsgp_plan_destroy(bsgp_plan* p) {
 
 int bsgp_plan_get_info(const bsgp_plan* p, bsgp_plan_info* info) {
     if (!p || !info) return fail(BSGP_E_ARG, "NULL argument");
-    info->ny = p->ny; info->nx = p->nx; info->dtype = p->dtype; info->device = p->device;
+    info->ny = p->img_ny; info->nx = p->img_nx; info->dtype = p->dtype; info->device = p->device;
+    info->grid_ny = p->ny; info->grid_nx = p->nx;
     info->cluster_size = p->g.G; info->num_clusters = p->num_clusters; info->threads = p->threads;
     info->smem_bytes = (int)p->smem_bytes; info->num_sms = p->num_sms; info->resident_mask = p->resident_mask;
     info->workspace_bytes = (long long)p->workspace_bytes;
@@ -699,16 +875,21 @@ int bsgp_plan_get_info(const bsgp_plan* p, bsgp_plan_info* info) {
 
 int bsgp_set_psf(bsgp_plan* p, const void* psf_dev, int n_psf, void* stream) {
     if (!p || !psf_dev || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
-    if (misaligned(psf_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
+    if (!p->embedded && misaligned(psf_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, (cudaStream_t)stream)
-                                : set_psf_t<float>(p, psf_dev, n_psf, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_enter(p, st);
+    if (rc) return rc;
+    if (p->embedded) rc = p->dtype == BSGP_F64 ? set_psf_wrapped<double>(p, psf_dev, n_psf, st) : set_psf_wrapped<float>(p, psf_dev, n_psf, st);
+    else rc = p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, st) : set_psf_t<float>(p, psf_dev, n_psf, st);
+    if (rc) return rc;
+    return plan_leave(p, st);
 }
 
 int bsgp_set_psf_host(bsgp_plan* p, const void* psf_host, int n_psf) {
     if (!p || !psf_host || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
     CU(cudaSetDevice(p->device));
-    const size_t bytes = (size_t)n_psf * p->ny * p->nx * p->elem;
+    const size_t bytes = (size_t)n_psf * p->img_ny * p->img_nx * p->elem;
     void* d = nullptr;
     CU(cudaMalloc(&d, bytes));
     cudaError_t e = cudaMemcpy(d, psf_host, bytes, cudaMemcpyHostToDevice);
@@ -720,10 +901,15 @@ int bsgp_set_psf_host(bsgp_plan* p, const void* psf_host, int n_psf) {
 
 int bsgp_set_psf_adjoint(bsgp_plan* p, const void* psf_dev, int n_psf, void* stream) {
     if (!p || !psf_dev || n_psf < 1) return fail(BSGP_E_ARG, "bad argument");
+    if (p->embedded) return fail(BSGP_E_STATE, "bsgp_set_psf_adjoint: a plan whose sides are not powers of two builds both kernels in bsgp_set_psf");
     if (misaligned(psf_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, (cudaStream_t)stream, true)
-                                : set_psf_t<float>(p, psf_dev, n_psf, (cudaStream_t)stream, true);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_enter(p, st);
+    if (rc) return rc;
+    rc = p->dtype == BSGP_F64 ? set_psf_t<double>(p, psf_dev, n_psf, st, true) : set_psf_t<float>(p, psf_dev, n_psf, st, true);
+    if (rc) return rc;
+    return plan_leave(p, st);
 }
 
 int bsgp_set_psf_adjoint_host(bsgp_plan* p, const void* psf_host, int n_psf) {
@@ -751,19 +937,26 @@ static int solve_checked(bsgp_plan* p, const bsgp_params* prm, int batch, const 
     if (prm->divergence == BSGP_DIV_BETA && !in->beta0) return fail(BSGP_E_ARG, "beta-divergence needs inputs.beta0");
     if (prm->init_recon == 1 && !in->x0) return fail(BSGP_E_ARG, "init_recon = 1 needs inputs.x0");
     if (prm->errflag && (!in->obj || !out->err)) return fail(BSGP_E_ARG, "errflag needs inputs.obj and outputs.err");
+    if (p->n_psf < 1) return fail(BSGP_E_STATE, "bsgp_set_psf has not been called");
     if (prm->adjoint_second_psf && (p->tf_adj == nullptr || p->n_psf_adj != p->n_psf))
         return fail(BSGP_E_STATE, "adjoint_second_psf set but bsgp_set_psf_adjoint was not called with the same number of PSFs");
+    if (p->embedded && (prm->region[1] > prm->region[0] || prm->region[3] > prm->region[2] || prm->adjoint_second_psf))
+        return fail(BSGP_E_ARG, "region / adjoint_second_psf (zero-padded operator) need a plan with power-of-two sides; embed the image into such a grid");
     if (prm->region[1] > prm->region[0] || prm->region[3] > prm->region[2]) {
         const int* r = prm->region;
         if (r[0] < 0 || r[1] > p->ny || r[2] < 0 || r[3] > p->nx || r[1] <= r[0] || r[3] <= r[2])
             return fail(BSGP_E_ARG, "region {%d, %d, %d, %d} does not fit the %dx%d grid", r[0], r[1], r[2], r[3], p->ny, p->nx);
         if (!(prm->div_a > 0.0) || !(prm->div_at > 0.0)) return fail(BSGP_E_ARG, "div_a / div_at must be positive when a region is set");
     }
-    if (misaligned(in->gn) || misaligned(out->x) || misaligned(in->x0) || misaligned(in->obj) || (in->bkg_is_image && misaligned(in->bkg)))
+    if (!p->embedded && (misaligned(in->gn) || misaligned(out->x) || misaligned(in->x0) || misaligned(in->obj) || (in->bkg_is_image && misaligned(in->bkg))))
         return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? solve_t<double>(p, prm, batch, in, out, (cudaStream_t)stream, ready)
-                                : solve_t<float>(p, prm, batch, in, out, (cudaStream_t)stream, ready);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = plan_enter(p, st);
+    if (rc) return rc;
+    rc = p->dtype == BSGP_F64 ? solve_t<double>(p, prm, batch, in, out, st, ready) : solve_t<float>(p, prm, batch, in, out, st, ready);
+    if (rc) return rc;
+    return plan_leave(p, st);
 }
 
 int bsgp_solve_batch(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out, void* stream) {
@@ -796,7 +989,7 @@ struct DevBuf {
 int bsgp_solve_batch_host(bsgp_plan* p, const bsgp_params* prm, int batch, const bsgp_inputs* in, const bsgp_outputs* out) {
     if (!p || !prm || !in || !out) return fail(BSGP_E_ARG, "NULL argument");
     CU(cudaSetDevice(p->device));
-    const size_t img = (size_t)p->ny * p->nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
+    const size_t img = (size_t)p->img_ny * p->img_nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
     DevBuf gn, bkg, flux, beta0, x0, obj, order, x, iters, status, discr, times, stopv, err, bfin, pe, lt, sc, ta, tl, tb, tt, te;
     int rc;
 #define TRY(e) do { rc = (e); if (rc) return rc; } while (0)
@@ -850,6 +1043,10 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
     if (batch < 1) return fail(BSGP_E_ARG, "batch must be >= 1");
     if (!in->gn || !in->bkg || !out->x || !out->iters || !out->status || !out->discr || !out->times) return fail(BSGP_E_ARG, "required pointer is NULL");
     CU(cudaSetDevice(p->device));
+    if (p->embedded) {                                             // wrapped plans: plain staging (upload, embed, solve, crop, download)
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        return bsgp_solve_batch_host(p, prm, batch, in, out);
+    }
     if (!page_locked(in->gn) || !page_locked(out->x) || !page_locked(in->x0) || !page_locked(in->obj) || (in->bkg_is_image && !page_locked(in->bkg)))
         return fail(BSGP_E_ARG, "bsgp_solve_batch_pinned needs page-locked image buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
     if (in->order) for (int i = 0; i < batch; ++i) if (in->order[i] < 0 || in->order[i] >= batch) return fail(BSGP_E_ARG, "inputs.order is not a permutation of 0..batch-1");
@@ -980,16 +1177,20 @@ int bsgp_apply_psf(bsgp_plan* p, const void* x_dev, void* y_dev, int batch, int 
     if (!p || !x_dev || !y_dev || batch < 1) return fail(BSGP_E_ARG, "bad argument");
     if (p->n_psf < 1) return fail(BSGP_E_STATE, "bsgp_set_psf has not been called");
     if (p->n_psf != 1 && p->n_psf != batch) return fail(BSGP_E_STATE, "%d PSFs set; need 1 or batch (%d)", p->n_psf, batch);
-    if (misaligned(x_dev) || misaligned(y_dev)) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
+    if (!p->embedded && (misaligned(x_dev) || misaligned(y_dev))) return fail(BSGP_E_ARG, "image pointers must be 16-byte aligned (vector loads)");
     CU(cudaSetDevice(p->device));
-    return p->dtype == BSGP_F64 ? apply_psf_t<double>(p, x_dev, y_dev, batch, adjoint, (cudaStream_t)stream)
-                                : apply_psf_t<float>(p, x_dev, y_dev, batch, adjoint, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = plan_enter(p, st);
+    if (rc) return rc;
+    rc = p->dtype == BSGP_F64 ? apply_psf_t<double>(p, x_dev, y_dev, batch, adjoint, st) : apply_psf_t<float>(p, x_dev, y_dev, batch, adjoint, st);
+    if (rc) return rc;
+    return plan_leave(p, st);
 }
 
 int bsgp_apply_psf_host(bsgp_plan* p, const void* x_host, void* y_host, int batch, int adjoint) {
     if (!p || !x_host || !y_host) return fail(BSGP_E_ARG, "NULL argument");
     CU(cudaSetDevice(p->device));
-    const size_t bytes = (size_t)batch * p->ny * p->nx * p->elem;
+    const size_t bytes = (size_t)batch * p->img_ny * p->img_nx * p->elem;
     DevBuf x, y;
     int rc;
     TRY(x.up(x_host, bytes)); TRY(y.alloc(true, bytes));
@@ -1000,19 +1201,19 @@ int bsgp_apply_psf_host(bsgp_plan* p, const void* x_host, void* y_host, int batc
 }
 
 int bsgp_project_df(const double* b, const double* c, const double* dia, int n, int batch, double sat_cap, double lambda0,
-                    double dlambda0, double tol_lam, int max_projs, double* x, int* evals, int* status, int device, void* stream) {
+                    double dlambda0, double tol_lam, int max_projs, int biter, int siter, double* x, int* evals, int* status, int device, void* stream) {
     if (!b || !c || !dia || !x || n < 1 || batch < 1) return fail(BSGP_E_ARG, "bad argument");
     CU(cudaSetDevice(device));
     const int has_cap = (sat_cap == sat_cap) && sat_cap >= 0.0;
     const int grid = batch < 4096 ? batch : 4096;
     bsgp_project_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(b, c, dia, n, batch, sat_cap, has_cap, lambda0, dlambda0, tol_lam,
-                                                                max_projs, x, evals, status);
+                                                                max_projs, biter, siter, x, evals, status);
     CU(cudaGetLastError());
     return BSGP_OK;
 }
 
 int bsgp_project_df_host(const double* b, const double* c, const double* dia, int n, int batch, double sat_cap, double lambda0,
-                         double dlambda0, double tol_lam, int max_projs, double* x, int* evals, int* status, int device) {
+                         double dlambda0, double tol_lam, int max_projs, int biter, int siter, double* x, int* evals, int* status, int device) {
     if (!b || !c || !dia || !x) return fail(BSGP_E_ARG, "NULL argument");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -1024,7 +1225,7 @@ int bsgp_project_df_host(const double* b, const double* c, const double* dia, in
     TRY(db.up(b, (size_t)batch * 8)); TRY(dc.up(c, vb)); TRY(dd.up(dia, vb)); TRY(dx.alloc(true, vb));
     TRY(de.alloc(true, (size_t)batch * 4)); TRY(ds.alloc(true, (size_t)batch * 4));
     TRY(bsgp_project_df((const double*)db.d, (const double*)dc.d, (const double*)dd.d, n, batch, sat_cap, lambda0, dlambda0, tol_lam,
-                        max_projs, (double*)dx.d, (int*)de.d, (int*)ds.d, device, nullptr));
+                        max_projs, biter, siter, (double*)dx.d, (int*)de.d, (int*)ds.d, device, nullptr));
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "projection kernel failed: %s", cudaGetErrorString(e));
     TRY(dx.down(x, vb)); TRY(de.down(evals, (size_t)batch * 4)); TRY(ds.down(status, (size_t)batch * 4));

@@ -74,6 +74,7 @@ inline bool make_geom(int ny, int nx, int G, size_t elem_bytes /* sizeof(cplx<T>
     g->ny = ny; g->nx = nx; g->hx = nx / 2;
     g->lg_nx = ilog2(nx); g->lg_ny = ilog2(ny); g->lg_hx = g->lg_nx - 1;
     g->G = G;
+    g->wrap_ny = g->wrap_nx = 0;
     if (ny % (2 * G) != 0 || (nx / 2) % G != 0) return false;
     g->rows_per_cta = ny / G;
     g->cols_per_cta = g->hx / G;

@@ -27,12 +27,14 @@ struct ProjResult {
 
 template <class Eval>
 BSGP_DEV ProjResult flux_rootfind(Eval& eval, double b, int max_projs, double lambda = 0.0, double dlambda = 1.0,
-                                  double tol_lam = 1e-11) {
+                                  double tol_lam = 1e-11, int biter0 = 0, int siter0 = 0) {
     ProjResult out;
     out.evals = 0;
     out.status = PROJ_OK;
     const double tol_r = 1e-11 * b;
-    int biter = 0, siter = 0;
+    // The caller's counters (:7) only matter through the secant budget: biter keeps growing during the bracketing
+    // (:39, :64), maxit_s = max_projs - biter is taken after it (:103) and the loop runs while siter < maxit_s (:106).
+    int biter = biter0, siter = siter0, nsteps = 0;
     double lam = lambda, dlam = dlambda, lam_lo, lam_hi, r_lo, r_hi, s;
 
     double r = eval(lam); ++out.evals;                                  // :22-25
@@ -49,7 +51,7 @@ BSGP_DEV ProjResult flux_rootfind(Eval& eval, double b, int max_projs, double la
             dlam = dlam + dlam / s;
             lam = lam + dlam;
             r_lo = r;
-            if (biter > kBracketCap || !is_finite(lam)) { out.status = PROJ_NO_BRACKET; out.lambda = lam_lo; return out; }
+            if (++nsteps > kBracketCap || !is_finite(lam)) { out.status = PROJ_NO_BRACKET; out.lambda = lam_lo; return out; }
             r = eval(lam); ++out.evals;
         }
         lam_hi = lam; r_hi = r;
@@ -66,7 +68,7 @@ BSGP_DEV ProjResult flux_rootfind(Eval& eval, double b, int max_projs, double la
             dlam = grown;
             lam = lam - dlam;
             r_hi = r;
-            if (biter > kBracketCap) { out.status = PROJ_NO_BRACKET; out.lambda = lam_hi; return out; }
+            if (++nsteps > kBracketCap) { out.status = PROJ_NO_BRACKET; out.lambda = lam_hi; return out; }
             r = eval(lam); ++out.evals;
         }
         lam_lo = lam; r_lo = r;

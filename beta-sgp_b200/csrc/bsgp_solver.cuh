@@ -346,7 +346,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, c
         st2(xtf, i, xt);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
@@ -383,7 +383,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_ri_grad0(Ctx ctx
         return (kind == 0) ? nsub((T)1, w) : nsub(p1, w);
     };
     auto ca = [&](int i, const In1<T>& in, V2<T> w) { st2(gr, i, mk2(one(inside<MK>(R, i), in.a.x, w.x), one(inside<MK>(R, i + 1), in.a.y, w.y))); };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
 }
 
 // consumer: bounds of the scaling matrix from y = flux/(flux+bkg) * A^T(gn)     sgp.py:268-270 / 712-714
@@ -401,7 +401,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R2 ph_ri_bounds(Ctx ctx,
         if (yv > hi) hi = yv;
     };
     auto ca = [&](int i, const In1<T>& in, V2<T> w) { one(inside<MK>(R, i), in.a.x, w.x); one(inside<MK>(R, i + 1), in.a.y, w.y); };
-    conv_rows_inverse<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<2, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R2 r; r.a = lo; r.b = hi;
     return r;
 }
@@ -508,7 +508,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, 
         st2(dtf, i, dt);
         st2(t1, i, p);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
@@ -595,7 +595,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R7 ph_ri_bb(Ctx ctx, con
         gnew.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y, in.e.y, w.y);
         st2(gr, i, gnew);
     };
-    conv_rows_inverse<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
+    conv_rows_inverse<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R7 r;
 #pragma unroll
     for (int k = 0; k < 7; ++k) r.v[k] = bb[k];

@@ -5,7 +5,10 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $BSGP_NVCC_FLAGS"
+# the library reports the hash of the sources it was built from (bsgp_version()); __graft_entry__.build() checks it,
+# so a stale binary cannot run unnoticed
+HASH=$(cat $(ls *.cu *.cuh *.h ../../include/bsgp.h | LC_ALL=C sort) | sha256sum | cut -c1-16)
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -DBSGP_SRC_HASH=\"$HASH\" $BSGP_NVCC_FLAGS"
 OUT=${BSGP_OUT:-libbsgp.so}
 B=build${BSGP_TAG:+_$BSGP_TAG}
 mkdir -p $B

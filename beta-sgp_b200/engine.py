@@ -48,11 +48,26 @@ class Plan:
         check(lib().bsgp_plan_get_info(self._h, C.byref(i)))
         return {f: getattr(i, f) for f, _ in i._fields_}
 
+    def _image_tensor(self, t, name, lead=None):
+        """Validate a CUDA tensor handed to the library as raw memory: [ny,nx] or [n,ny,nx] with the plan's image shape,
+        on the plan's device; converted to the plan's dtype and made contiguous.  `lead`: allowed leading sizes."""
+        import torch
+        if not t.is_cuda:
+            raise ValueError(f"{name} must be a CUDA tensor (or a numpy array)")
+        if (t.device.index or 0) != self.device:
+            raise ValueError(f"{name} lives on {t.device}, the plan on cuda:{self.device}")
+        if t.dim() not in (2, 3) or tuple(t.shape[-2:]) != (self.ny, self.nx):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}; expected [{self.ny},{self.nx}] or [n,{self.ny},{self.nx}]")
+        n = 1 if t.dim() == 2 else int(t.shape[0])
+        if lead is not None and n not in lead:
+            raise ValueError(f"{name} has {n} images; expected one of {sorted(set(lead))}")
+        want = torch.float64 if self.dtype == "float64" else torch.float32
+        return t.to(want).contiguous(), n
+
     def set_psf(self, psf):
         """psf: numpy [ny,nx] / [n,ny,nx] or a CUDA tensor of the same shapes."""
         if _is_tensor(psf):
-            t = psf.contiguous()
-            n = 1 if t.dim() == 2 else t.shape[0]
+            t, n = self._image_tensor(psf, "psf")
             check(lib().bsgp_set_psf(self._h, t.data_ptr(), n, _stream_ptr()))
             self._psf_keepalive = t
             return n
@@ -67,8 +82,7 @@ class Plan:
     def set_psf_adjoint(self, psf):
         """Second kernel, used for A^T by the zero-padded operator (sgp.py:157); numpy or CUDA tensor, [ny,nx] / [n,ny,nx]."""
         if _is_tensor(psf):
-            t = psf.contiguous()
-            n = 1 if t.dim() == 2 else t.shape[0]
+            t, n = self._image_tensor(psf, "adjoint psf")
             check(lib().bsgp_set_psf_adjoint(self._h, t.data_ptr(), n, _stream_ptr()))
             self._psf_adj_keepalive = t
             return n
@@ -82,6 +96,8 @@ class Plan:
     def apply_psf(self, x, adjoint=False):
         """A(x) / AT(x) for numpy [ny,nx] or [n,ny,nx] (sgp.py:111-120)."""
         a = np.ascontiguousarray(x, dtype=_NP[self.dtype])
+        if a.ndim not in (2, 3) or a.shape[-2:] != (self.ny, self.nx):
+            raise ValueError(f"x has shape {a.shape}; expected [{self.ny},{self.nx}] or [n,{self.ny},{self.nx}]")
         n = 1 if a.ndim == 2 else a.shape[0]
         y = np.empty_like(a)
         check(lib().bsgp_apply_psf_host(self._h, a.ctypes.data, y.ctypes.data, n, int(bool(adjoint))))
@@ -103,6 +119,10 @@ _plans = {}
 
 
 def get_plan(ny, nx, dtype="float64", device=0, cluster_size=0, threads=0):
+    """Process-wide plan cache, one plan per (shape, dtype, device, tuning).  A plan holds mutable device state (PSF
+    spectra, scratch, work queue); the library serialises the launches of one plan on the device (an event chained
+    through every entry point, include/bsgp.h "Streams"), so sharing a cached plan between CUDA streams is safe but
+    not concurrent: callers that want overlap create their own `Plan` per stream."""
     key = (int(ny), int(nx), str(dtype), int(device), int(cluster_size), int(threads))
     p = _plans.get(key)
     if p is None:
@@ -241,6 +261,11 @@ def solve_batch(gn, psf, bkg, divergence="beta", flux=None, betaParam=1.005, x0=
     b0 = np.ascontiguousarray(np.broadcast_to(np.asarray(betaParam, dtype=np.float64).reshape(-1), (B,)))
     x0a = None if x0 is None else np.ascontiguousarray(x0, dtype=npdt)
     obja = None if obj is None else np.ascontiguousarray(obj, dtype=npdt)
+    for name, a in (("x0", x0a), ("obj", obja)):
+        if a is not None and a.shape != gn.shape:
+            raise ValueError(f"{name} has shape {a.shape}; expected the shape of gn {gn.shape}")
+    if (plan.ny, plan.nx) != (ny, nx) or plan.dtype != dtype:
+        raise ValueError(f"plan is for {plan.ny}x{plan.nx} {plan.dtype} images, gn is {ny}x{nx} {dtype}")
     if p.init_recon == 1 and x0a is None:
         raise ValueError("init_recon=1 needs x0 (the sgp()/sgp_betaDiv() wrappers draw it with seed 42)")
     T = p.maxit + 1
@@ -324,26 +349,47 @@ def _solve_batch_device(gn, psf, bkg, divergence, flux, betaParam, x0, obj, trac
     if not gn.is_cuda:
         raise BsgpError("tensor inputs must live on a CUDA device (there is no CPU path)")
     dev = gn.device
+    if gn.dtype not in (torch.float64, torch.float32):
+        raise ValueError("gn must be float64 or float32")
     dtype = {torch.float64: "float64", torch.float32: "float32"}[gn.dtype]
+    if gn.dim() != 3:
+        raise ValueError("gn must be [batch, ny, nx]")
     gn = gn.contiguous()
     B, ny, nx = gn.shape
     p = _params(divergence, kw, flux is not None)
     plan = plan or get_plan(ny, nx, dtype, dev.index or 0)
+    if (plan.ny, plan.nx) != (ny, nx) or plan.dtype != dtype or plan.device != (dev.index or 0):
+        raise ValueError(f"plan is for {plan.ny}x{plan.nx} {plan.dtype} images on cuda:{plan.device}, gn is {ny}x{nx} {dtype} on {dev}")
+
+    def image_stack(t, name):
+        """[B,ny,nx] tensor of gn's dtype on gn's device (raw pointers go to the library: a short or foreign array would be read out of bounds)"""
+        if t is None:
+            return None
+        if not _is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(t), device=dev)
+        if t.device != dev or tuple(t.shape) != (B, ny, nx):
+            raise ValueError(f"{name} must have the shape {(B, ny, nx)} of gn and live on {dev}; got {tuple(t.shape)} on {t.device}")
+        return t.to(gn.dtype).contiguous()
+
     with torch.cuda.device(dev):
         if not psf_is_set:
             n_psf = plan.set_psf(psf if _is_tensor(psf) else torch.as_tensor(np.ascontiguousarray(psf), dtype=gn.dtype, device=dev))
             if n_psf not in (1, B):
                 raise ValueError("psf must be one image or one per batch entry")
         if _is_tensor(bkg) and bkg.dim() == 3:
-            bkg_img, bkg_t = 1, bkg.contiguous()
+            bkg_img, bkg_t = 1, image_stack(bkg, "bkg")
         else:
             bkg_img = 0
             bkg_t = (bkg if _is_tensor(bkg) else torch.as_tensor(np.asarray(bkg, dtype=np.float64), device=dev)).to(gn.dtype).reshape(-1).expand(B).contiguous()
         f64 = dict(dtype=torch.float64, device=dev)
         fl = None if flux is None else (flux if _is_tensor(flux) else torch.as_tensor(np.asarray(flux, dtype=np.float64), device=dev)).to(torch.float64).reshape(-1).expand(B).contiguous()
         b0 = (betaParam if _is_tensor(betaParam) else torch.as_tensor(np.asarray(betaParam, dtype=np.float64), device=dev)).to(torch.float64).reshape(-1).expand(B).contiguous()
-        x0t = None if x0 is None else x0.contiguous()
-        objt = None if obj is None else obj.contiguous()
+        x0t, objt = image_stack(x0, "x0"), image_stack(obj, "obj")
+        if p.init_recon == 1 and x0t is None:
+            raise ValueError("init_recon=1 needs x0 (the sgp()/sgp_betaDiv() wrappers draw it with seed 42)")
+        for name, t in (("bkg", bkg_t), ("flux", fl), ("betaParam", b0)):
+            if t is not None and t.device != dev:
+                raise ValueError(f"{name} lives on {t.device}, gn on {dev}")
         T = p.maxit + 1
         i32 = dict(dtype=torch.int32, device=dev)
         out = dict(x=torch.empty_like(gn), iters=torch.zeros(B, **i32), status=torch.zeros(B, **i32),
@@ -387,6 +433,8 @@ def _solve_batch_pinned(gn, psf, bkg, divergence, flux, betaParam, x0, obj, devi
     B, ny, nx = gn.shape
     p = _params(divergence, kw, flux is not None)
     plan = plan or get_plan(ny, nx, dtype, device)
+    if (plan.ny, plan.nx) != (ny, nx) or plan.dtype != dtype:
+        raise ValueError(f"plan is for {plan.ny}x{plan.nx} {plan.dtype} images, gn is {ny}x{nx} {dtype}")
     with torch.cuda.device(plan.device):
         if not psf_is_set:
             psf_t = psf if _is_tensor(psf) else torch.as_tensor(np.ascontiguousarray(psf))
@@ -446,15 +494,19 @@ def _solve_batch_pinned(gn, psf, bkg, divergence, flux, betaParam, x0, obj, devi
                            ptr(tr["alpha"]) if tr else None, ptr(tr["lam"]) if tr else None, ptr(tr["beta"]) if tr else None,
                            ptr(tr["trials"]) if tr else None, ptr(tr["evals"]) if tr else None)
         check(lib().bsgp_solve_batch_pinned(plan.handle, C.byref(p), B, C.byref(ci), C.byref(co), _stream_ptr()))
+    for i in np.nonzero(out["status"] == _capi.ST_INPUT_TIMEOUT)[0]:      # skipped images: defined (zero) pixels, status says why
+        x[int(i)].zero_()
     return BatchResult(x=x, trace=tr, **out)
 
 
-def project_batch(b, c, dia, sat_cap=None, lambda_=0.0, dlambda_=1.0, tol_lam=1e-11, max_projs=1000, device=0):
+def project_batch(b, c, dia, sat_cap=None, lambda_=0.0, dlambda_=1.0, tol_lam=1e-11, max_projs=1000, biter=0, siter=0, device=0):
     """projectDF for a batch of problems: c, dia [B,n]; b [B] (flux_conserve_proj.py:7-144)."""
     c = np.ascontiguousarray(c, dtype=np.float64)
     dia = np.ascontiguousarray(dia, dtype=np.float64)
     if c.ndim == 1:
         c, dia = c[None], dia[None]
+    if c.ndim != 2 or dia.shape != c.shape:
+        raise ValueError(f"c and dia must both be [B, n]; got {c.shape} and {dia.shape}")
     B, n = c.shape
     b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64).reshape(-1), (B,)))
     x = np.empty_like(c)
@@ -462,5 +514,6 @@ def project_batch(b, c, dia, sat_cap=None, lambda_=0.0, dlambda_=1.0, tol_lam=1e
     st = np.zeros(B, np.int32)
     cap = float("nan") if sat_cap is None else float(sat_cap)
     check(lib().bsgp_project_df_host(b.ctypes.data, c.ctypes.data, dia.ctypes.data, n, B, cap, float(lambda_), float(dlambda_),
-                                     float(tol_lam), int(max_projs), x.ctypes.data, ev.ctypes.data, st.ctypes.data, int(device)))
+                                     float(tol_lam), int(max_projs), int(biter), int(siter), x.ctypes.data, ev.ctypes.data, st.ctypes.data,
+                                     int(device)))
     return x, ev, st

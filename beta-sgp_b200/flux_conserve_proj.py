@@ -29,9 +29,10 @@ def projectDF(b, c, dia, scaling, ccd_sat_level=None, lambda_=0, dlambda_=1, tol
     dia = np.asarray(dia).astype(np.float64, copy=False)
     b = float(np.asarray(b).astype(np.float64, copy=False))
     cap = None if ccd_sat_level is None else ccd_sat_level / scaling - EPSILON
-    # biter / siter only enter through the secant budget max_projs - biter and the test siter < budget
+    # biter / siter are the initial values of the reference's counters: biter grows during the bracketing, the secant
+    # budget is max_projs - biter afterwards (:103) and the loop runs while siter < budget (:106); the device code keeps both
     x, _, st = engine.project_batch(b, c.ravel(), dia.ravel(), sat_cap=cap, lambda_=lambda_, dlambda_=dlambda_,
-                                    tol_lam=tol_lam, max_projs=max_projs - biter - siter, device=DEVICE)
+                                    tol_lam=tol_lam, max_projs=max_projs, biter=biter, siter=siter, device=DEVICE)
     if int(st[0]) != 0:
         raise RuntimeError("projectDF: the multiplier could not be bracketed (the reference loops forever here)")
     return x[0].reshape(c.shape)

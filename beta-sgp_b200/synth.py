@@ -89,6 +89,38 @@ def star_stamps(count, size=32, seed=12345):
     return dict(gn=gn, psf=psf, bkg=sky.copy(), flux=flux, beta0=beta0, obj=obj)
 
 
+def star_cutouts(count, psf, seed=31):
+    """Star cut-outs of the PSF's own shape with ONE PSF shared by all of them: the literal call shape of
+    application_sgp_star_stamps.py:24,58,82-89 (31 x 31 cut-outs restored with the subdivision's 31 x 31 PSF image,
+    e.g. the one the reference ships as psf/psfccfbrd210048_1_1_img.fits).  One star within +-2 px of the centre,
+    flux 10^U[4,5.5], sky U[50,800], Poisson noise; the image is formed with the reference's own operator
+    (circular, fftshift placement: sgp.py:109-117), whatever the parity of the side.
+    Returns dict(gn[B,n,n], psf[n,n], bkg[B], flux[B], beta0[B], obj[B,n,n])."""
+    psf = np.asarray(psf, dtype=np.float64)
+    ny, nx = psf.shape
+    rng = np.random.default_rng(seed)
+    off = rng.uniform(-2.0, 2.0, (count, 2))
+    amp = 10.0 ** rng.uniform(4.0, 5.5, count)
+    sky = rng.uniform(50.0, 800.0, count)
+    obj = np.zeros((count, ny, nx))
+    for i in range(count):
+        y, x = ny // 2 + off[i, 0], nx // 2 + off[i, 1]
+        y0, x0 = int(np.floor(y)), int(np.floor(x))
+        fy, fx = y - y0, x - x0
+        obj[i, y0, x0] += amp[i] * (1 - fy) * (1 - fx)
+        obj[i, y0, x0 + 1] += amp[i] * (1 - fy) * fx
+        obj[i, y0 + 1, x0] += amp[i] * fy * (1 - fx)
+        obj[i, y0 + 1, x0 + 1] += amp[i] * fy * fx
+    tf = np.fft.fftn(np.fft.fftshift(psf))
+    mean = np.maximum(np.real(np.fft.ifftn(tf * np.fft.fftn(obj, axes=(-2, -1)), axes=(-2, -1))), 0.0) + sky[:, None, None]
+    gn = rng.poisson(mean).astype(np.float64)
+    flux = (gn - sky[:, None, None]).sum(axis=(1, 2))
+    assert np.all(flux > 0), "generator produced a cut-out with non-positive flux"
+    b5 = beta_inits()
+    beta0 = np.array([b5[i % 5] for i in range(count)])
+    return dict(gn=gn, psf=psf, bkg=sky.copy(), flux=flux, beta0=beta0, obj=obj)
+
+
 def crowded_field(size=2048, seed=2024, density=1.0 / 400.0, fwhm=3.5, tile=256):
     """A crowded frame: stars of flux 10^U[3,5], sky 300 + smooth gradient, Moffat PSF.
     Returns dict(frame, sky, truth, psf_tile) where psf_tile is the PSF embedded at

@@ -93,7 +93,8 @@ def reconstruct_full_image_from_patches(tiles, origins, shape, feather=None, dev
     return out
 
 
-def restore_frame(frame, psf, bkg, subdiv_shape=(256, 256), overlap=0, betaParam=1.005, divergence="beta", feather=None, device=0, **kw):
+def restore_frame(frame, psf, bkg, subdiv_shape=(256, 256), overlap=0, betaParam=1.005, divergence="beta", feather=None, device=0,
+                  on_failure="raise", **kw):
     """Frame in, frame out: tiles of `subdiv_shape` (powers of two for the circular operator) are cut on the device, restored
     in one persistent-kernel launch (each tile conserves its own flux sum(gn - bkg), the solver's default, sgp.py:661-666)
     and cross-faded back.  `bkg` is a scalar or a background map of the frame's shape; `psf` has the tile's shape.
@@ -109,5 +110,21 @@ def restore_frame(frame, psf, bkg, subdiv_shape=(256, 256), overlap=0, betaParam
     kw.setdefault("proj_type", 1)
     # flux = None: every tile conserves its own sum(gn - bkg), the default of sgp.py:207-211 / 661-666
     res = solve_batch(gn, psf, bk, divergence=divergence, betaParam=betaParam, **kw)
+    # A tile that was not restored must not be blended into the frame silently: with proj_type=1 a background-only
+    # tile whose sum(gn - bkg) is not positive ends with BSGP_ST_BAD_FLUX (the reference raises ValueError at
+    # sgp.py:269/713 for it).  on_failure="raise" (default) reports the tiles; "keep_input" substitutes the observed tile.
+    status = res.status.cpu().numpy()
+    bad = np.nonzero(status != 0)[0]
+    if bad.size:
+        from ._capi import STATUS_TEXT
+        what = ", ".join(f"tile {int(i)} at {tuple(int(v) for v in org[i])}: {STATUS_TEXT.get(int(status[i]), status[i])}" for i in bad[:8])
+        if on_failure == "raise":
+            raise ValueError(f"{bad.size} of {len(status)} tiles were not restored ({what}); pass on_failure='keep_input' to keep the observed tiles there")
+        if on_failure != "keep_input":
+            raise ValueError("on_failure must be 'raise' or 'keep_input'")
+        import warnings
+        warnings.warn(f"{bad.size} of {len(status)} tiles were not restored and keep their observed pixels ({what})")
+        idx = torch.as_tensor(bad, device=gn.device)
+        res.x[idx] = gn[idx]
     out = reconstruct_full_image_from_patches(res.x, org, frame.shape, feather, device)
     return out, res, org

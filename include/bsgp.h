@@ -15,6 +15,18 @@
  * pointers, run asynchronously on `stream` (a cudaStream_t passed as void*) and never synchronise.
  * Images are row-major [batch][ny][nx] in the plan's dtype.  There is no CPU fallback: without a
  * CUDA device every compute entry point fails with BSGP_E_CUDA.
+ *
+ * Shapes.  Any ny x nx (the reference's numpy closure accepts any size, sgp.py:108-120; its star-stamp application
+ * uses 31 x 31 cut-outs, application_sgp_star_stamps.py:24,58).  Sides that are powers of two in [16, 8192] run on
+ * their own FFT grid and need 16-byte aligned image pointers; any other side n <= 4096 runs on a grid of side
+ * 2^k >= 2n - 1 ("wrapped plan": linear convolution + fold, exactly the circular operator with the reference's
+ * np.fft.fftshift placement, including its one-pixel offset for odd n); the library moves the caller's arrays to and
+ * from that grid itself and only needs element alignment.
+ *
+ * Streams.  A plan owns mutable device state (PSF spectra, scratch, the work queue).  Launches on one plan are
+ * serialised on the device: every device entry point makes `stream` wait for the plan's previous launch (an event),
+ * so one plan may be used from several streams; use one plan per stream for concurrency.  Buffers passed to an
+ * asynchronous call must stay alive until that call's work has completed.
  */
 #ifndef BSGP_H
 #define BSGP_H
@@ -118,9 +130,11 @@ typedef struct bsgp_plan_info {
     int num_sms;
     int resident_mask;     /* bit b set: per-image buffer b lives in shared memory */
     long long workspace_bytes;
+    int grid_ny, grid_nx;  /* the power-of-two FFT grid (== ny, nx unless the plan is wrapped) */
 } bsgp_plan_info;
 
-/* One plan per (shape, dtype, device): twiddle tables, per-cluster scratch, PSF spectra. */
+/* One plan per (shape, dtype, device): twiddle tables, per-cluster scratch, PSF spectra.  Any shape with sides in
+ * [1, 8192] (powers of two) or [1, 4096] (other sizes, see "Shapes" above). */
 int bsgp_plan_create(int ny, int nx, int dtype, int device, bsgp_plan** plan);
 int bsgp_plan_destroy(bsgp_plan* plan);
 int bsgp_plan_get_info(const bsgp_plan* plan, bsgp_plan_info* info);
@@ -133,7 +147,8 @@ int bsgp_plan_configure(bsgp_plan* plan, int cluster_size, int threads);
  * the whole batch) or the batch size (one PSF per image). */
 int bsgp_set_psf(bsgp_plan* plan, const void* psf_dev, int n_psf, void* stream);
 int bsgp_set_psf_host(bsgp_plan* plan, const void* psf_host, int n_psf);
-/* Second kernel for A^T (sgp.py:157: convolve_fft(x, psf.conj().T, ...)); same n_psf as bsgp_set_psf. */
+/* Second kernel for A^T (sgp.py:157: convolve_fft(x, psf.conj().T, ...)); same n_psf as bsgp_set_psf.  Power-of-two
+ * plans only (BSGP_E_STATE otherwise: wrapped plans use both spectra for the circular operator itself). */
 int bsgp_set_psf_adjoint(bsgp_plan* plan, const void* psf_dev, int n_psf, void* stream);
 int bsgp_set_psf_adjoint_host(bsgp_plan* plan, const void* psf_host, int n_psf);
 
@@ -158,13 +173,16 @@ int bsgp_apply_psf(bsgp_plan* plan, const void* x_dev, void* y_dev, int batch, i
 int bsgp_apply_psf_host(bsgp_plan* plan, const void* x_host, void* y_host, int batch, int adjoint);
 
 /* projectDF (flux_conserve_proj.py:7): `batch` independent problems of length n, fp64.
- * sat_cap < 0 or NaN: no upper clamp; else x <= sat_cap (the caller passes ccd_sat_level/scaling - eps). */
+ * sat_cap < 0 or NaN: no upper clamp; else x <= sat_cap (the caller passes ccd_sat_level/scaling - eps).
+ * lambda0, dlambda0, tol_lam, biter, siter, max_projs: the reference's keyword arguments of the same names; biter
+ * and siter are the initial values of its two counters (the secant budget is max_projs - biter AFTER the bracketing,
+ * flux_conserve_proj.py:103, and the loop runs while siter < budget, :106). */
 int bsgp_project_df(const double* b_dev, const double* c_dev, const double* dia_dev, int n, int batch, double sat_cap,
-                    double lambda0, double dlambda0, double tol_lam, int max_projs, double* x_dev, int* evals_dev,
-                    int* status_dev, int device, void* stream);
+                    double lambda0, double dlambda0, double tol_lam, int max_projs, int biter, int siter, double* x_dev,
+                    int* evals_dev, int* status_dev, int device, void* stream);
 int bsgp_project_df_host(const double* b, const double* c, const double* dia, int n, int batch, double sat_cap,
-                         double lambda0, double dlambda0, double tol_lam, int max_projs, double* x, int* evals,
-                         int* status, int device);
+                         double lambda0, double dlambda0, double tol_lam, int max_projs, int biter, int siter, double* x,
+                         int* evals, int* status, int device);
 
 /* betaDiv(y, x, beta) (sgp.py:441-458): three partial sums -> out[0]; betaDivDeriv (sgp.py:462-495)
  * per element -> deriv (may be NULL).  fp64, host pointers. */

@@ -34,6 +34,8 @@ def case_inputs(name, fixtures, golden):
     if dkey.startswith("tile"):
         base = f"tile{(int(dkey[4:]) // 5) * 5}"
         gn, psf, bkg = fixtures[base + "/gn"], fixtures["tile0/psf"], fixtures[base + "/bkg"]
+    elif dkey.startswith("cutout31_"):
+        gn, psf, bkg = fixtures[dkey + "/gn"], fixtures["cutout31_0/psf"], fixtures[dkey + "/bkg"]
     else:
         gn, psf, bkg = fixtures[dkey + "/gn"], fixtures[dkey + "/psf"], fixtures[dkey + "/bkg"]
     if name + "/flux_in" in golden.files:

@@ -50,9 +50,10 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x0=None, psf_adjoint=None, **kw):
+def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x0=None, psf_adjoint=None, wrapped=False, **kw):
     """Emulated solve of one image; keyword arguments as sgp()/sgp_betaDiv() (+ region / div_a / div_at /
-    adjoint_second_psf with psf_adjoint for the zero-padded operator: inputs already embedded in the grid)."""
+    adjoint_second_psf with psf_adjoint for the zero-padded operator: inputs already embedded in the grid).
+    wrapped=True: any image size through the wrapped-plan steps of the library (bsgp_wrap.h)."""
     L = lib()
     ny, nx = gn.shape
     gn = np.ascontiguousarray(gn, dtype=np.float64)
@@ -75,10 +76,16 @@ def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x
     objc = None if obj is None else np.ascontiguousarray(obj, dtype=np.float64)
     x0c = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
     pa = None if psf_adjoint is None else np.ascontiguousarray(psf_adjoint, dtype=np.float64)
-    L.emul_solve.argtypes = [C.c_int, C.c_int, C.POINTER(capi.Params)] + [C.c_void_p] * 3 + [C.c_void_p, C.c_int] + [C.c_void_p] * 19
-    rc = L.emul_solve(ny, nx, C.byref(p), _p(gn), _p(psf), _p(pa), _p(bkg), bkg_is_image, _p(fl), _p(b0), _p(x0c), _p(objc),
-                      _p(x), _p(iters), _p(status), _p(discr), _p(stopv), _p(err), _p(bfin), _p(pe), _p(lt), _p(sc),
-                      _p(ta), _p(tl), _p(tb), _p(tt), _p(te))
+    if wrapped:
+        L.emul_solve_wrapped.argtypes = [C.c_int, C.c_int, C.POINTER(capi.Params)] + [C.c_void_p] * 2 + [C.c_void_p, C.c_int] + [C.c_void_p] * 19
+        rc = L.emul_solve_wrapped(ny, nx, C.byref(p), _p(gn), _p(psf), _p(bkg), bkg_is_image, _p(fl), _p(b0), _p(x0c), _p(objc),
+                                  _p(x), _p(iters), _p(status), _p(discr), _p(stopv), _p(err), _p(bfin), _p(pe), _p(lt), _p(sc),
+                                  _p(ta), _p(tl), _p(tb), _p(tt), _p(te))
+    else:
+        L.emul_solve.argtypes = [C.c_int, C.c_int, C.POINTER(capi.Params)] + [C.c_void_p] * 3 + [C.c_void_p, C.c_int] + [C.c_void_p] * 19
+        rc = L.emul_solve(ny, nx, C.byref(p), _p(gn), _p(psf), _p(pa), _p(bkg), bkg_is_image, _p(fl), _p(b0), _p(x0c), _p(objc),
+                          _p(x), _p(iters), _p(status), _p(discr), _p(stopv), _p(err), _p(bfin), _p(pe), _p(lt), _p(sc),
+                          _p(ta), _p(tl), _p(tb), _p(tt), _p(te))
     assert rc == 0
     n = int(iters[0])
     return dict(x=x, iters=n, status=int(status[0]), discr=discr[:n + 1], stop_value=stopv[:n + 1], err=err,
@@ -86,14 +93,14 @@ def solve(gn, psf, bkg, divergence="kl", flux=None, betaParam=1.005, obj=None, x
                 alpha=ta[1:n + 1], lam=tl[1:n + 1], beta_trace=tb[1:n + 1], trials=tt[1:n + 1], evals=te[1:n + 1])
 
 
-def project(c, dia, b, sat_cap=None, max_projs=1000):
+def project(c, dia, b, sat_cap=None, max_projs=1000, biter=0, siter=0):
     L = lib()
     c = np.ascontiguousarray(c, dtype=np.float64); dia = np.ascontiguousarray(dia, dtype=np.float64)
     x = np.zeros_like(c); ev = C.c_int(0)
-    L.emul_project.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
+    L.emul_project.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.POINTER(C.c_int)]
     st = L.emul_project(_p(c), _p(dia), c.size, float(b), 0.0 if sat_cap is None else float(sat_cap),
-                        int(sat_cap is not None), max_projs, _p(x), C.byref(ev))
+                        int(sat_cap is not None), max_projs, int(biter), int(siter), _p(x), C.byref(ev))
     return x, ev.value, st
 
 

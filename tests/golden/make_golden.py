@@ -25,7 +25,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(ROOT, "beta-sgp_b200"))
 
 import reference_loader  # noqa: E402
-from cases import CASES, N_STAMPS, N_TILES  # noqa: E402
+from cases import CASES, N_CUTOUTS31, N_STAMPS, N_TILES  # noqa: E402
 import synth  # noqa: E402
 from oracle import sgp_oracle as orc  # noqa: E402
 
@@ -41,6 +41,15 @@ def build_inputs():
     for i in range(N_STAMPS):
         data[f"stamp{i}"] = dict(gn=st["gn"][i], psf=st["psf"][i], bkg=np.float64(st["bkg"][i]),
                                  flux=float(st["flux"][i]), betaParam=float(st["beta0"][i]))
+    # 31 x 31 cut-outs with the PSF image the reference ships (read by make_psf_golden.py into psf_golden.npz)
+    sys.path.insert(0, HERE)
+    from make_psf_golden import read_fits_f64
+    psf31 = read_fits_f64("/root/reference/psf/psfccfbrd210048_1_1_img.fits")
+    assert psf31.shape == (31, 31)
+    co = synth.star_cutouts(N_CUTOUTS31, psf31, seed=31)
+    for i in range(N_CUTOUTS31):
+        data[f"cutout31_{i}"] = dict(gn=co["gn"][i], psf=psf31, bkg=np.float64(co["bkg"][i]),
+                                     flux=float(co["flux"][i]), betaParam=float(co["beta0"][i]))
     tl = synth.field_tiles(size=1024, tile=256, seed=2024, n_beta=5, max_tiles=N_TILES)
     for i in range(N_TILES * 5):
         data[f"tile{i}"] = dict(gn=tl["gn"][i], psf=tl["psf"], bkg=tl["bkg"][i], flux=float(tl["flux"][i]),
@@ -59,6 +68,8 @@ def main():
             if f in d:
                 if f == "psf" and key.startswith("tile") and key != "tile0":
                     continue               # one shared PSF for all tiles
+                if f == "psf" and key.startswith("cutout31_") and key != "cutout31_0":
+                    continue               # ... and for all cut-outs
                 fixtures[f"{key}/{f}"] = np.asarray(d[f])
     scratch = tempfile.mkdtemp()
     os.chdir(scratch)                      # the reference writes ./sgp.log
@@ -67,7 +78,8 @@ def main():
         kw = dict(kw)
         if "flux" in d:
             kw["flux"] = np.float64(d["flux"])
-            kw["betaParam"] = d["betaParam"]
+            if div == "beta":
+                kw["betaParam"] = d["betaParam"]
         fn = ref_sgp.sgp if div == "kl" else ref_sgp.sgp_betaDiv
         out = io.StringIO()
         with contextlib.redirect_stdout(out):

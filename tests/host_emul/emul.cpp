@@ -12,6 +12,7 @@
 
 #include "../../beta-sgp_b200/csrc/bsgp_plan.h"
 #include "../../beta-sgp_b200/csrc/bsgp_solver.cuh"
+#include "../../beta-sgp_b200/csrc/bsgp_wrap.h"
 
 using namespace bsgp;
 
@@ -80,10 +81,34 @@ template <typename T, class C = HostCtx> struct HostPlan {
                 auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(y + off, i, v); };
                 if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
                 else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
-                else conv_rows_inverse<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), cf, ca);
+                else conv_rows_inverse<2, true>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), cf, ca);
             }
     }
+    // wrapped plan (bsgp_wrap.h): grid kernels of A / A^T from the caller's iny x inx PSF, fold widths in the geometry
+    void make_tf_wrapped(const T* psf, int iny, int inx) {
+        const int ny = g.ny, nx = g.nx;
+        std::vector<T> k((size_t)ny * nx);
+        for (int adj = 0; adj < 2; ++adj) {
+            for (int r = 0; r < ny; ++r)
+                for (int c = 0; c < nx; ++c) {
+                    int sr, sc;
+                    k[(size_t)r * nx + c] = wrap_psf_source(r, c, ny, nx, iny, inx, adj, &sr, &sc) ? psf[(size_t)sr * inx + sc] : (T)0;
+                }
+            make_tf(k.data(), adj ? &tf_adj : nullptr);
+        }
+        g.wrap_ny = ny != iny ? iny : 0;
+        g.wrap_nx = nx != inx ? inx : 0;
+    }
 };
+
+template <typename T> static void embed(const T* src, int iny, int inx, T* dst, int ny, int nx) {
+    for (int r = 0; r < ny; ++r)
+        for (int c = 0; c < nx; ++c) dst[(size_t)r * nx + c] = (r < iny && c < inx) ? src[(size_t)r * inx + c] : (T)0;
+}
+template <typename T> static void crop(const T* src, int ny, int nx, T* dst, int iny, int inx) {
+    for (int r = 0; r < iny; ++r)
+        for (int c = 0; c < inx; ++c) dst[(size_t)r * inx + c] = src[(size_t)r * nx + c];
+}
 
 extern "C" {
 
@@ -127,6 +152,21 @@ int emul_conv(int ny, int nx, int G, long long ws_limit, const double* x, const 
     if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
     pl.make_tf(psf);
     pl.apply(x, y, adjoint);
+    return 0;
+}
+
+// arbitrary-size circular operator: the host-side steps of a wrapped plan (bsgp_kernels.cu) around the same device code
+int emul_conv_wrapped(int iny, int inx, int G, long long ws_limit, const double* x, const double* psf, int adjoint, double* y) {
+    const int ny = wrap_grid_side(iny), nx = wrap_grid_side(inx);
+    if (ny > kMaxSide || nx > kMaxSide) return 2;
+    HostPlan<double> pl;
+    if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
+    pl.make_tf_wrapped(psf, iny, inx);
+    std::vector<double> xe((size_t)ny * nx), ye((size_t)ny * nx);
+    embed(x, iny, inx, xe.data(), ny, nx);
+    if (adjoint) pl.tf.swap(pl.tf_adj);               // A^T = CONV_TF with the spectrum of h~
+    pl.apply(xe.data(), ye.data(), 0);
+    crop(ye.data(), ny, nx, y, iny, inx);
     return 0;
 }
 
@@ -180,8 +220,49 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     return 0;
 }
 
+// full solver on a wrapped plan: what solve_t does for plan->embedded (embed, region = image window, both spectra, crop)
+int emul_solve_wrapped(int iny, int inx, const bsgp_params* params, const double* gn, const double* psf, const double* bkg,
+                       int bkg_is_image, const double* flux, const double* beta0, const double* x0, const double* obj,
+                       double* x_out, int* iters, int* status, double* discr, double* stop_value, double* err, double* beta_final,
+                       int* proj_evals, int* ls_trials, double* scalars, double* tr_alpha, double* tr_lambda, double* tr_beta,
+                       int* tr_trials, int* tr_evals) {
+    const int ny = wrap_grid_side(iny), nx = wrap_grid_side(inx);
+    if (ny > kMaxSide || nx > kMaxSide) return 2;
+    HostPlan<double> pl;
+    if (!pl.init(ny, nx, 1, (size_t)1 << 30)) return 1;
+    pl.make_tf_wrapped(psf, iny, inx);
+    const size_t npix = (size_t)ny * nx;
+    std::vector<double> work(NBUF * npix, 0.0), times(params->maxit + 1, 0.0), gne(npix), bke(npix), x0e(npix), obe(npix), xe(npix);
+    embed(gn, iny, inx, gne.data(), ny, nx);
+    if (bkg_is_image) embed(bkg, iny, inx, bke.data(), ny, nx);
+    if (x0) embed(x0, iny, inx, x0e.data(), ny, nx);
+    if (obj) embed(obj, iny, inx, obe.data(), ny, nx);
+    double* buf[NBUF];
+    for (int b = 0; b < NBUF; ++b) buf[b] = work.data() + b * npix;
+    SolveArgs<double> a;
+    memset(&a, 0, sizeof(a));
+    a.p = *params;
+    a.p.region[0] = 0; a.p.region[1] = iny; a.p.region[2] = 0; a.p.region[3] = inx; a.p.div_a = a.p.div_at = 1.0; a.p.adjoint_second_psf = 1;
+    a.g = pl.g; a.batch = 1;
+    a.gn = gne.data(); a.bkg = bkg_is_image ? bke.data() : bkg; a.bkg_is_image = bkg_is_image; a.flux = flux; a.beta0 = beta0;
+    a.x0 = x0 ? x0e.data() : nullptr; a.obj = obj ? obe.data() : nullptr;
+    a.twx = pl.twx.data(); a.twy = pl.twy.data(); a.tf = pl.tf.data(); a.tf_adj = pl.tf_adj.data(); a.n_psf = 1;
+    a.x_out = xe.data(); a.iters = iters; a.status = status; a.discr = discr; a.times = times.data();
+    a.stop_value = stop_value; a.err = err; a.beta_final = beta_final; a.proj_evals = proj_evals; a.ls_trials = ls_trials;
+    a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
+    a.tr_evals = tr_evals;
+    HostCtx ctx;
+    ImgState<double> S;
+    memset(&S, 0, sizeof(S));
+    S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem; S.tw_split = 0;
+    pl.bind();
+    solve_image<double, true>(ctx, a, &S, buf, pl.tf.data(), pl.tf_adj.data(), 0);
+    crop(xe.data(), ny, nx, x_out, iny, inx);
+    return 0;
+}
+
 // projectDF root-find with the reference's x = (c + lambda) / dia evaluation
-int emul_project(const double* c, const double* dia, int n, double b, double sat_cap, int has_cap, int max_projs,
+int emul_project(const double* c, const double* dia, int n, double b, double sat_cap, int has_cap, int max_projs, int biter, int siter,
                  double* x, int* evals) {
     auto point = [&](int i, double lam) {
         double v = ndiv(nadd(c[i], lam), dia[i]);
@@ -194,7 +275,7 @@ int emul_project(const double* c, const double* dia, int n, double b, double sat
         for (int i = 0; i < n; ++i) s += point(i, lam);
         return s - b;
     };
-    ProjResult pr = flux_rootfind(eval, b, max_projs);
+    ProjResult pr = flux_rootfind(eval, b, max_projs, 0.0, 1.0, 1e-11, biter, siter);
     for (int i = 0; i < n; ++i) x[i] = point(i, pr.lambda);
     *evals = pr.evals;
     return pr.status;

@@ -9,7 +9,7 @@ part 1 explains why the 332-iteration runs and beta = 1.0001 are not, and what i
 import numpy as np
 import pytest
 
-from cases import CASES, STRICT
+from cases import CASES, CUTOUT_CASES, SENSITIVE, STRICT
 
 pytestmark = pytest.mark.gpu
 
@@ -39,9 +39,12 @@ def _run(bs, name, get_case, **extra):
 # ------------------------------------------------------------------------------------------------
 # pieces
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(32, 32), (64, 64), (128, 128), (256, 256), (512, 512), (64, 256), (1024, 1024)])
+@pytest.mark.parametrize("shape", [(32, 32), (64, 64), (128, 128), (256, 256), (512, 512), (64, 256), (1024, 1024),
+                                   (31, 31), (33, 20), (5, 7), (32, 31), (100, 75), (375, 375), (450, 450)])
 def test_psf_operator_matches_numpy(bs, shape):
-    """A / A^T closures (sgp.py:108-120): real(ifftn(TF * fftn(x))), TF = fftn(fftshift(psf))."""
+    """A / A^T closures (sgp.py:108-120): real(ifftn(TF * fftn(x))), TF = fftn(fftshift(psf)).  Sides that are not
+    powers of two (31: application_sgp_star_stamps.py:24; 375 / 450: the paper's sub-frames) run on wrapped plans and
+    must reproduce the odd-size fftshift offset."""
     rng = np.random.default_rng(shape[0] + shape[1])
     n = 5
     x = rng.normal(size=(n,) + shape)
@@ -88,6 +91,17 @@ def test_projectDF_known_answers(bs, golden):
         assert x.min() >= 0.0
 
 
+@pytest.mark.parametrize("mp,bi,si", [(4, 0, 0), (4, 2, 0), (6, 0, 3), (5, 1, 2)])
+def test_projectDF_counter_arguments(bs, golden, mp, bi, si):
+    """biter / siter / max_projs as the reference budgets them (flux_conserve_proj.py:39,64,103,106), against the oracle."""
+    from oracle import sgp_oracle as orc
+    for k in ("proj02", "proj06", "proj10"):
+        b, c, dia = np.float64(golden[k + "/b"]), golden[k + "/c"], golden[k + "/dia"]
+        xo = orc.flux_projection(b, c.copy(), dia.copy(), 1.0, max_projs=mp, biter=bi, siter=si)
+        x = bs.projectDF(b, c, dia, 1.0, max_projs=mp, biter=bi, siter=si)
+        np.testing.assert_allclose(x, xo, rtol=1e-9, atol=1e-12)
+
+
 def test_projectDF_edge_cases(bs):
     b = np.float64(3.0)
     x = bs.projectDF(b, np.array([1.0, 1.0, 1.0]), np.ones(3), 1.0)         # already feasible: early return
@@ -121,19 +135,20 @@ def test_beta_divergence_helpers(bs, golden, fixtures):
 # ------------------------------------------------------------------------------------------------
 # the solver against the reference's vectors
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", STRICT + [f"stamp{i:02d}" for i in range(16)])
+@pytest.mark.parametrize("name", STRICT + [f"stamp{i:02d}" for i in range(16)] + CUTOUT_CASES)
 def test_strict_parity(bs, name, get_case, golden):
     r = _run(bs, name, get_case)
     it = int(golden[name + "/iters"])
     assert int(r.status[0]) == 0
     assert int(r.iters[0]) == it
     ref = golden[name + "/discr"]
-    assert np.abs(r.discr[0, :it + 1] - ref).max() <= 1e-10 * np.abs(ref).max()
+    tol_d, tol_x = SENSITIVE.get(name, (1e-10, 1e-8))          # 1e-10 / 1e-8 except where the reference itself is not reproducible to it
+    assert np.abs(r.discr[0, :it + 1] - ref).max() <= tol_d * np.abs(ref).max()
     xs = golden[name + "/x_sub"]
-    assert np.abs(r.x[0][::8, ::8] - xs).max() <= 1e-8 * np.abs(xs).max()
+    assert np.abs(r.x[0][::8, ::8] - xs).max() <= tol_x * np.abs(xs).max()
     if name + "/x" in golden.files:
         xr = golden[name + "/x"]
-        assert np.abs(r.x[0] - xr).max() <= 1e-8 * np.abs(xr).max()
+        assert np.abs(r.x[0] - xr).max() <= tol_x * np.abs(xr).max()
     assert np.array_equal(r.trace["evals"][0, 1:it + 1], golden[name + "/proj_evals"])
     # line searches take the reference's number of trials, except where the step degenerated to the
     # lam < 1e-12 escape (sgp.py:336): there fv - fr is rounding noise in the reference as well
@@ -141,6 +156,44 @@ def test_strict_parity(bs, name, get_case, golden):
     assert np.array_equal(r.trace["trials"][0, 1:it][real], golden[name + "/trials"][:it - 1][real])
     if CASES[name][1] == "beta":
         assert float(r.beta_final[0]) == pytest.approx(float(golden[name + "/beta_final"]), rel=1e-9)
+
+
+def test_star_stamp_application_call_31x31(bs, get_case, golden, tmp_path, monkeypatch, capsys):
+    """The literal call of application_sgp_star_stamps.py:82-89 / :107-113 through the drop-in entry points: a 31 x 31
+    cut-out, the 31 x 31 PSF image the reference ships, the default (numpy) operator.  Then the same cut-outs as one
+    batch (shared PSF), from numpy, device tensors and pinned host tensors: identical to the single calls."""
+    import torch
+    monkeypatch.chdir(tmp_path)
+    from cases import _cutout_kw, _cutout_kl_kw
+    for name in ("cutout31_02", "cutout31_kl_03"):
+        gn, psf, bkg, div, kw = get_case(name)
+        assert gn.shape == (31, 31) and psf.shape == (31, 31)
+        if div == "beta":
+            x, it, discr, times, err = bs.sgp_betaDiv(gn, psf, bkg, flux=kw["flux"], betaParam=kw["betaParam"], save=False, **_cutout_kw)
+            assert "No. of iterations" in capsys.readouterr().out
+        else:
+            x, it, discr, times, err = bs.sgp(gn, psf, bkg, flux=kw["flux"], save=False, **_cutout_kl_kw)
+        assert err is None and it == int(golden[name + "/iters"]) and x.shape == (31, 31)
+        assert discr.shape == (it + 1,) and times.shape == (it + 1,)
+        np.testing.assert_allclose(discr, golden[name + "/discr"], rtol=1e-10)
+        xr = golden[name + "/x"]
+        assert np.abs(x - xr).max() <= 1e-8 * np.abs(xr).max()
+        assert abs(x.sum() - float(kw["flux"])) <= 1e-9 * float(kw["flux"])
+    names = [f"cutout31_{i:02d}" for i in range(10)]
+    cs = [get_case(n) for n in names]
+    gn = np.stack([c[0] for c in cs]); psf = cs[0][1]
+    bkg = np.array([float(c[2]) for c in cs]); flux = np.array([float(c[4]["flux"]) for c in cs]); b0 = np.array([c[4]["betaParam"] for c in cs])
+    r = bs.sgp_betaDiv_batch(gn, psf, bkg, flux=flux, betaParam=b0, **_cutout_kw)
+    for i, n in enumerate(names):
+        assert int(r.iters[i]) == int(golden[n + "/iters"]) and int(r.status[i]) == 0
+        xr = golden[n + "/x"]
+        assert np.abs(r.x[i] - xr).max() <= SENSITIVE.get(n, (0, 1e-8))[1] * np.abs(xr).max()
+    dev = torch.device("cuda", 0)
+    rd = bs.sgp_betaDiv_batch(torch.as_tensor(gn, device=dev), torch.as_tensor(psf, device=dev), torch.as_tensor(bkg, device=dev),
+                              flux=torch.as_tensor(flux, device=dev), betaParam=torch.as_tensor(b0, device=dev), **_cutout_kw)
+    assert np.array_equal(rd.iters.cpu().numpy(), r.iters) and np.array_equal(rd.x.cpu().numpy(), r.x)
+    rp = bs.sgp_betaDiv_batch(torch.as_tensor(gn).pin_memory(), psf, bkg, flux=flux, betaParam=b0, **_cutout_kw)
+    assert np.array_equal(np.asarray(rp.iters), r.iters) and np.array_equal(rp.x.numpy(), r.x)
 
 
 @pytest.mark.parametrize("name", [f"tile{i:02d}" for i in range(10)] + ["sat_beta_p1_stop3", "ngc_beta_adapt"])

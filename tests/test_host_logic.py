@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import emul_helper as eh
-from cases import CASES, STRICT
+from cases import CASES, SENSITIVE, STRICT
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 capi = eh.capi
@@ -106,7 +106,8 @@ def test_emulated_projection_known_answers(golden):
 
 EMUL_CASES = ["ngc_kl_27", "ngc_beta_p1_stop3", "ngc_kl_p1_stop2", "ngc_kl_stop2_quiet", "ngc_kl_stop4", "ngc_kl_init0",
               "ngc_kl_init1_p1", "ngc_kl_noscale_flux", "ngc_kl_nonmonotone", "sat_kl_default_stop", "ngc_beta_adapt",
-              "ngc_beta_is", "ngc_beta_one", "ngc_beta_two", "stamp00", "stamp01", "stamp06", "stamp10", "tile00", "tile07"]
+              "ngc_beta_is", "ngc_beta_one", "ngc_beta_two", "stamp00", "stamp01", "stamp06", "stamp10", "tile00", "tile07",
+              "cutout31_00", "cutout31_04", "cutout31_07", "cutout31_kl_03"]
 
 
 @pytest.mark.parametrize("name", EMUL_CASES)
@@ -114,13 +115,14 @@ def test_emulated_solver_matches_reference(name, get_case, golden):
     """bsgp_solver.cuh run as one emulated CTA: identical iteration counts, projection-evaluation counts
     and stopping decisions; objective trace and image within the north-star tolerances."""
     gn, psf, bkg, div, kw = get_case(name)
-    r = eh.solve(gn, psf, bkg, divergence=div, **kw)
+    r = eh.solve(gn, psf, bkg, divergence=div, wrapped=name.startswith("cutout31"), **kw)      # 31 x 31: wrapped plan
     assert r["status"] == 0
     assert r["iters"] == int(golden[name + "/iters"])
     ref = golden[name + "/discr"]
-    assert np.abs(r["discr"] - ref).max() <= 1e-10 * np.abs(ref).max()
+    tol_d, tol_x = SENSITIVE.get(name, (1e-10, 1e-8))
+    assert np.abs(r["discr"] - ref).max() <= tol_d * np.abs(ref).max()
     xs = golden[name + "/x_sub"]
-    assert np.abs(r["x"][::8, ::8] - xs).max() <= 1e-8 * np.abs(xs).max()
+    assert np.abs(r["x"][::8, ::8] - xs).max() <= tol_x * np.abs(xs).max()
     assert np.array_equal(r["evals"], golden[name + "/proj_evals"])
     assert r["proj_evals"] == int(golden[name + "/proj_evals"].sum() + golden[name + "/init_proj_evals"])
     n = r["iters"]
@@ -265,3 +267,72 @@ def test_psf_model_file_parsing(tmp_path):
     assert p.ntot == 36 and len(p.coeffs) == 36
     row = p.params()
     assert row.shape == (5 + 12,) and np.array_equal(row[5:], g["file_values"][14:26])
+
+
+@pytest.mark.parametrize("ny,nx,G,ws", [(31, 31, 1, 1 << 20), (31, 31, 2, 1 << 20), (33, 20, 1, 1 << 20), (48, 48, 4, 1 << 20),
+                                        (5, 7, 1, 1 << 20), (32, 31, 1, 1 << 20), (31, 64, 2, 40 * 1024), (100, 75, 8, 72 * 1024),
+                                        (375, 375, 8, 72 * 1024), (450, 450, 8, 160 * 1024)])
+def test_emulated_wrapped_convolution(ny, nx, G, ws):
+    """Sides that are not powers of two (sgp.py:108-120 accepts any size; application_sgp_star_stamps.py:24 uses 31):
+    linear convolution on a 2^k >= 2n-1 grid + fold == the reference's circular operator, odd-size fftshift offset
+    included."""
+    L = eh.lib()
+    L.emul_conv_wrapped.argtypes = [C.c_int] * 3 + [C.c_longlong, P, P, C.c_int, P]
+    rng = np.random.default_rng(ny * 1000 + nx + G)
+    x = rng.normal(size=(ny, nx))
+    psf = rng.random((ny, nx))
+    psf /= psf.sum()
+    tf = np.fft.fftn(np.fft.fftshift(psf))
+    for adjoint in (0, 1):
+        y = np.zeros((ny, nx))
+        assert L.emul_conv_wrapped(ny, nx, G, ws, x.ctypes.data_as(P), psf.ctypes.data_as(P), adjoint, y.ctypes.data_as(P)) == 0
+        ref = np.real(np.fft.ifftn((np.conj(tf) if adjoint else tf) * np.fft.fftn(x)))
+        assert np.abs(y - ref).max() <= 1e-14 * np.abs(ref).max()
+
+
+def _stamp31(seed, n=31):
+    """A 31 x 31 cut-out in the shape of application_sgp_star_stamps.py:58-89 (synthetic: one star, Poisson noise, sky)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_synth_t", os.path.join(ROOT, "beta-sgp_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    rng = np.random.default_rng(seed)
+    psf = synth.moffat_psf(n, n, rng.uniform(2.5, 4.5), 2.5, rng.uniform(1.0, 1.3), rng.uniform(0, np.pi))
+    obj = np.zeros((n, n))
+    obj[n // 2 + rng.integers(-2, 3), n // 2 + rng.integers(-2, 3)] = 10.0 ** rng.uniform(4.0, 5.5)
+    sky = rng.uniform(50.0, 800.0)
+    tf = np.fft.fftn(np.fft.fftshift(psf))
+    gn = rng.poisson(np.maximum(np.real(np.fft.ifftn(tf * np.fft.fftn(obj))), 0.0) + sky).astype(np.float64)
+    return gn, psf, np.float64(sky), np.float64((gn - sky).sum())
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulated_wrapped_solver_matches_oracle(seed):
+    """beta-SGP with the stamp application's keyword set on a 31 x 31 cut-out: same iteration count, trial and
+    projection-evaluation counts, discr <= 1e-10, image <= 1e-8 against the oracle (numpy closure of any size)."""
+    from oracle import sgp_oracle as orc
+    gn, psf, bkg, flux = _stamp31(seed)
+    kw = dict(gamma=1e-4, beta=0.4, alpha_min=1e-5, alpha_max=1e5, alpha=1e1, M_alpha=3, tau=0.5, M=1, proj_type=1, max_projs=1000,
+              init_recon=2, stop_criterion=3, verbose=True, ccd_sat_level=65000, scale_data=True, lr=1e-3, lr_exp_param=0.1,
+              schedule_lr=True, adapt_beta=True, MAXIT=500)
+    b0 = [1.0882026172983832, 1.0248357076505616, 0.9789][seed % 3]
+    o = orc.solve(gn, psf, bkg, divergence="beta", flux=flux, betaParam=b0, **kw)
+    r = eh.solve(gn, psf, bkg, divergence="beta", flux=flux, betaParam=b0, wrapped=True, **kw)
+    assert r["status"] == 0 and r["iters"] == o.iters
+    assert list(r["trials"]) == list(o.trace.trials) and list(r["evals"]) == list(o.trace.proj_evals)
+    assert np.abs(r["discr"] - o.discr).max() <= 1e-10 * np.abs(o.discr).max()
+    assert np.abs(r["x"] - o.x).max() <= 1e-8 * np.abs(o.x).max()
+
+
+@pytest.mark.parametrize("mp,bi,si", [(1000, 0, 0), (4, 0, 0), (4, 2, 0), (6, 0, 3), (5, 1, 2), (3, 3, 0)])
+def test_emulated_projection_counter_arguments(golden, mp, bi, si):
+    """projectDF's biter / siter / max_projs keywords (flux_conserve_proj.py:7): the secant budget is max_projs - biter
+    with biter still growing during the bracketing (:39,:64,:103), the loop runs while siter < budget (:106)."""
+    from oracle import sgp_oracle as orc
+    for k in ("proj02", "proj06", "proj10"):              # the cases with the longest secant phases (8-12 evaluations)
+        b, c, dia = np.float64(golden[k + "/b"]), golden[k + "/c"], golden[k + "/dia"]
+        cnt = []
+        xo = orc.flux_projection(b, c.copy(), dia.copy(), 1.0, max_projs=mp, biter=bi, siter=si, counter=cnt)
+        xe, ev, st = eh.project(c, dia, float(b), max_projs=mp, biter=bi, siter=si)
+        assert st == 0 and ev == cnt[-1]
+        np.testing.assert_allclose(xe, xo, rtol=1e-12, atol=1e-15)
