@@ -120,6 +120,7 @@ def lib():
     if hasattr(L, "bsgp_psf_model_eval"):
         L.bsgp_psf_model_eval.argtypes = [vp, ip, ip, ip, ip, ip, ip, ip, vp, ip, vp]
     L.bsgp_device_count.restype = ip
+    L.bsgp_launch_count.restype = C.c_longlong
     L.bsgp_last_error_string.restype = C.c_char_p
     L.bsgp_version.restype = C.c_char_p
     _lib = L
@@ -134,5 +135,5 @@ def check(rc):
 
 EXPORTED = ["bsgp_plan_create", "bsgp_plan_destroy", "bsgp_plan_get_info", "bsgp_plan_configure", "bsgp_set_psf",
             "bsgp_set_psf_host", "bsgp_set_psf_adjoint", "bsgp_set_psf_adjoint_host", "bsgp_solve_batch", "bsgp_solve_batch_host", "bsgp_solve_batch_pinned", "bsgp_apply_psf", "bsgp_apply_psf_host",
-            "bsgp_project_df", "bsgp_project_df_host", "bsgp_tile_boxes", "bsgp_extract_tiles", "bsgp_assemble_tiles", "bsgp_psf_model_eval", "bsgp_beta_div_host", "bsgp_beta_grad_terms_host", "bsgp_device_count",
+            "bsgp_project_df", "bsgp_project_df_host", "bsgp_tile_boxes", "bsgp_extract_tiles", "bsgp_assemble_tiles", "bsgp_psf_model_eval", "bsgp_beta_div_host", "bsgp_beta_grad_terms_host", "bsgp_device_count", "bsgp_launch_count",
             "bsgp_last_error_string", "bsgp_version"]

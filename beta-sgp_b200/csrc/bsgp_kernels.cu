@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -352,6 +353,9 @@ __global__ void bsgp_psf_model_kernel(const double* __restrict__ params, int str
 }
 
 static thread_local std::string g_err;
+// kernels launched by this library since it was loaded (bsgp_launch_count): what a caller reports as "my kernels ran"
+static std::atomic<long long> g_launches{0};
+static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static int fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -634,6 +638,7 @@ static int data_grid(int device, size_t total, int* blocks) {
 template <typename T> static int embed_images(bsgp_plan* p, const void* src, void* dst, size_t count, cudaStream_t st) {
     int blocks = 0, rc = data_grid(p->device, count * p->ny * p->nx, &blocks);
     if (rc) return rc;
+    count_launch();
     bsgp_embed_images_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, p->img_ny, p->img_nx, (T*)dst, p->ny, p->nx, count);
     CU(cudaGetLastError());
     return BSGP_OK;
@@ -641,6 +646,7 @@ template <typename T> static int embed_images(bsgp_plan* p, const void* src, voi
 template <typename T> static int crop_images(bsgp_plan* p, const void* src, void* dst, size_t count, cudaStream_t st) {
     int blocks = 0, rc = data_grid(p->device, count * p->img_ny * p->img_nx, &blocks);
     if (rc) return rc;
+    count_launch();
     bsgp_crop_images_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, p->ny, p->nx, (T*)dst, p->img_ny, p->img_nx, count);
     CU(cudaGetLastError());
     return BSGP_OK;
@@ -651,6 +657,7 @@ template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int c
         unsigned og = p->conv_off_geom, op = p->conv_off_ppx, ow = p->conv_off_ws;
         double* gp = p->gpart;
         void* args[] = {&a, &og, &op, &ow, &gp};
+        count_launch();
         cudaError_t e = cudaLaunchCooperativeKernel(conv_frame_kernel_ptr<T>(), dim3(p->g.G), dim3(512), args, p->conv_smem, st);
         if (e != cudaSuccess) return fail(BSGP_E_CUDA, "convolution kernel launch failed: %s", cudaGetErrorString(e));
         return BSGP_OK;
@@ -660,6 +667,7 @@ template <typename T> static int launch_conv(bsgp_plan* p, ConvArgs<T>& a, int c
     LaunchCfg lc{nclu * p->g.G, 512, p->g.G, p->conv_smem, st};
     unsigned og = p->conv_off_geom, op = p->conv_off_ppx, ow = p->conv_off_ws;
     void* args[] = {&a, &og, &op, &ow};
+    count_launch();
     cudaError_t e = launch_clustered(conv_kernel_ptr<T>(), lc, args);
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "convolution kernel launch failed: %s", cudaGetErrorString(e));
     return BSGP_OK;
@@ -712,6 +720,7 @@ template <typename T> static int set_psf_wrapped(bsgp_plan* p, const void* psf_d
     rc = data_grid(p->device, (size_t)n_psf * p->ny * p->nx, &blocks);
     if (rc) return rc;
     for (int adj = 0; adj < 2; ++adj) {
+        count_launch();
         bsgp_embed_psf_kernel<T><<<blocks, 256, 0, st>>>((const T*)psf_dev, p->img_ny, p->img_nx, (T*)p->emb_psf, p->ny, p->nx, (size_t)n_psf, adj);
         CU(cudaGetLastError());
         rc = set_psf_t<T>(p, p->emb_psf, n_psf, st, adj != 0);
@@ -776,6 +785,7 @@ static int solve_grid(bsgp_plan* p, const bsgp_params* prm, int batch, const bsg
     if (p->frame) {
         LaunchCfg fc{p->g.G, 512, 1, p->smem_bytes, st, 1};
         const bool mk = prm->region[1] > prm->region[0];
+        count_launch();
         cudaError_t fe = mk ? launch_frame<T, true>(fc, a, p->sp, p->tf_stride, p->gpart) : launch_frame<T, false>(fc, a, p->sp, p->tf_stride, p->gpart);
         if (fe != cudaSuccess) return fail(BSGP_E_CUDA, "frame kernel launch failed: %s", cudaGetErrorString(fe));
         return BSGP_OK;
@@ -784,6 +794,7 @@ static int solve_grid(bsgp_plan* p, const bsgp_params* prm, int batch, const bsg
     const int nclu = batch < p->num_clusters ? batch : p->num_clusters;
     LaunchCfg lc{nclu * p->g.G, p->threads, p->g.G, p->smem_bytes, st, p->minb};
     const bool mk = prm->region[1] > prm->region[0];
+    count_launch();
     cudaError_t e = mk ? launch_solve<T, true>(lc, a, p->sp, p->tf_stride) : launch_solve<T, false>(lc, a, p->sp, p->tf_stride);
     if (e != cudaSuccess) return fail(BSGP_E_CUDA, "solve kernel launch failed: %s", cudaGetErrorString(e));
     return BSGP_OK;
@@ -809,6 +820,7 @@ int bsgp_device_count(void) {
     return n;
 }
 const char* bsgp_last_error_string(void) { return g_err.c_str(); }
+long long bsgp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 #ifndef BSGP_SRC_HASH
 #define BSGP_SRC_HASH "unknown"
 #endif
@@ -1206,6 +1218,7 @@ int bsgp_project_df(const double* b, const double* c, const double* dia, int n, 
     CU(cudaSetDevice(device));
     const int has_cap = (sat_cap == sat_cap) && sat_cap >= 0.0;
     const int grid = batch < 4096 ? batch : 4096;
+    count_launch();
     bsgp_project_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(b, c, dia, n, batch, sat_cap, has_cap, lambda0, dlambda0, tol_lam,
                                                                 max_projs, biter, siter, x, evals, status);
     CU(cudaGetLastError());
@@ -1243,6 +1256,7 @@ int bsgp_beta_div_host(const double* y, const double* x, long long n, double bet
     long long want = (n + 255) / 256;
     const int grid = (int)(want < 592 ? want : 592);
     TRY(dy.up(y, (size_t)n * 8)); TRY(dx.up(x, (size_t)n * 8)); TRY(dp.alloc(true, (size_t)grid * 3 * 8)); TRY(dd.alloc(deriv != nullptr, (size_t)n * 8));
+    count_launch();
     bsgp_betadiv_kernel<<<grid, 256>>>((const double*)dy.d, (const double*)dx.d, n, beta, (double*)dp.d, (double*)dd.d);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -1269,6 +1283,7 @@ int bsgp_beta_grad_terms_host(const double* den, const double* gn, long long n, 
     int rc;
     TRY(dd.up(den, (size_t)n * 8)); TRY(dg.up(gn, (size_t)n * 8)); TRY(dp.alloc(true, (size_t)n * 8)); TRY(du.alloc(true, (size_t)n * 8));
     long long want = (n + 255) / 256;
+    count_launch();
     bsgp_betagrad_kernel<<<(int)(want < 1184 ? want : 1184), 256>>>((const double*)dd.d, (const double*)dg.d, n, beta, (double*)dp.d, (double*)du.d);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -1321,6 +1336,7 @@ int bsgp_extract_tiles(const void* frame_dev, int height, int width, int dtype, 
     CU(cudaSetDevice(device));
     int blocks = 0, rc = tile_grid(device, (size_t)n * tile_h * tile_w, &blocks);
     if (rc) return rc;
+    count_launch();
     if (dtype == BSGP_F64) bsgp_extract_tiles_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)frame_dev, height, width, origins_dev, n, tile_h, tile_w, (double*)tiles_dev);
     else bsgp_extract_tiles_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)frame_dev, height, width, origins_dev, n, tile_h, tile_w, (float*)tiles_dev);
     CU(cudaGetLastError());
@@ -1333,6 +1349,7 @@ int bsgp_assemble_tiles(const void* tiles_dev, const int* origins_dev, int n, in
     CU(cudaSetDevice(device));
     int blocks = 0, rc = tile_grid(device, (size_t)height * width, &blocks);
     if (rc) return rc;
+    count_launch();
     if (dtype == BSGP_F64) bsgp_assemble_tiles_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (double*)frame_dev, height, width);
     else bsgp_assemble_tiles_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)tiles_dev, origins_dev, n, tile_h, tile_w, feather, (float*)frame_dev, height, width);
     CU(cudaGetLastError());
@@ -1347,6 +1364,7 @@ int bsgp_psf_model_eval(const double* params_dev, int n, int ngauss, int hw, int
     if (dtype != BSGP_F64 && dtype != BSGP_F32) return fail(BSGP_E_ARG, "bad dtype");
     CU(cudaSetDevice(device));
     const int stride = 5 + 6 * ngauss;
+    count_launch();
     if (dtype == BSGP_F64) bsgp_psf_model_kernel<double><<<n, 256, 0, (cudaStream_t)stream>>>(params_dev, stride, ngauss, hw, ny, nx, normalize, (double*)out_dev);
     else bsgp_psf_model_kernel<float><<<n, 256, 0, (cudaStream_t)stream>>>(params_dev, stride, ngauss, hw, ny, nx, normalize, (float*)out_dev);
     CU(cudaGetLastError());

@@ -131,6 +131,29 @@ def get_plan(ny, nx, dtype="float64", device=0, cluster_size=0, threads=0):
     return p
 
 
+# Width of the CTA configuration as a function of the number of images a GPU holds (measured on B200, 256 x 256 beta-SGP,
+# tools/latency_probe.py): the default (clusters of 8 CTAs x 128 threads, 4 CTAs of different images per SM, 71 images in
+# flight) has the best throughput but 200 us per iteration of ONE image; 16 x 128 reaches 118 us and 8 x 256 112 us with
+# 31 / 15 images in flight, 16 x 256 74 us with 7.  A GPU that holds fewer images than slots is bounded by its longest solve,
+# so it trades slots for latency.  (threshold on images per default slot, (cluster_size, threads)); first match wins.
+_WIDTH_RULES = ((1.7, (0, 0)), (0.7, (16, 128)), (0.11, (0, 256)), (0.0, (16, 256)))
+
+
+def auto_config(ny, nx, batch, dtype="float64"):
+    """(cluster_size, threads) for `batch` images of ny x nx on one GPU; (0, 0) = the library's default."""
+    npix = int(ny) * int(nx)
+    pow2 = all(v >= 16 and v & (v - 1) == 0 for v in (int(ny), int(nx)))
+    if not pow2 or npix * (8 if dtype == "float64" else 4) <= 64 * 1024 or npix >= (1 << 20):
+        return (0, 0)                                   # stamps (one CTA each), wrapped plans and frame mode: one configuration
+    slots = 71.0                                        # images in flight of the default configuration on 148 SMs
+    for thr, cfg in _WIDTH_RULES:
+        if batch >= thr * slots:
+            if cfg[0] == 16 and not (ny % 64 == 0 and (nx // 2) % 32 == 0):
+                continue
+            return cfg
+    return (0, 0)
+
+
 def clear_plans():
     for p in _plans.values():
         p.close()

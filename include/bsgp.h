@@ -216,6 +216,8 @@ int bsgp_psf_model_eval(const double* params_dev, int n, int ngauss, int hw, int
                         void* out_dev, int device, void* stream);
 
 int bsgp_device_count(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (all plans, all streams). */
+long long bsgp_launch_count(void);
 const char* bsgp_last_error_string(void);
 const char* bsgp_version(void);
 

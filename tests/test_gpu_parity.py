@@ -332,6 +332,27 @@ def test_full_size_stamp_batch_properties(bs):
         assert np.abs(r.x[i] - o.x).max() <= 1e-8 * np.abs(o.x).max(), i
 
 
+def test_full_size_bench_field_against_oracle(bs):
+    """BASELINE config 4 at full size, the exact field bench.py times (2048^2, seed 2024 -> 64 tiles x 5 beta inits = 320
+    solves, 2-D background, shared PSF): all statuses OK, flux conserved, and a random sample of 10 solves (two per beta
+    init) against the oracle: identical iteration counts, image <= 1e-8.  The total iteration count of the field
+    (13 780 with the oracle) is what bench.py's algorithmic-byte count rests on."""
+    from oracle import sgp_oracle as orc
+    w = bs.synth.field_tiles(size=2048, tile=256, seed=2024, n_beta=5)
+    kw = dict(bs.synth.TILE_KWARGS)
+    r = bs.sgp_betaDiv_batch(w["gn"], w["psf"], w["bkg"], flux=w["flux"], betaParam=w["beta0"], **kw)
+    assert len(r.iters) == 320 and np.all(r.status == 0)
+    assert np.abs(r.x.sum(axis=(1, 2)) - w["flux"]).max() <= 1e-9 * w["flux"].max()
+    assert int(r.iters.sum()) == 13780 and int(r.iters.max()) == 119
+    rng = np.random.default_rng(4)
+    sample = [int(5 * t + b) for b in range(5) for t in rng.choice(64, 2, replace=False)]
+    for i in sample:
+        o = orc.solve(w["gn"][i], w["psf"], w["bkg"][i], divergence="beta", flux=np.float64(w["flux"][i]), betaParam=float(w["beta0"][i]), **kw)
+        assert int(r.iters[i]) == o.iters, i
+        assert np.abs(r.x[i] - o.x).max() <= 1e-8 * np.abs(o.x).max(), i
+        assert int(r.proj_evals[i]) == int(np.sum(o.trace.proj_evals) + o.trace.init_proj_evals), i
+
+
 def test_fp32_mode_tolerance(bs, get_case, golden):
     """Optional fp32 mode: flux and image within 1e-4 relative; iteration-count drift reported, not asserted."""
     for name in ("ngc_kl_27", "ngc_beta_p1_27"):
@@ -473,6 +494,39 @@ def test_sharded_front_end_single_rank(bs, fixtures, golden):
     a = bs.sgp_betaDiv_batch(gn, psf, bkg, flux=flux, betaParam=b0, **bs.synth.STAMP_KWARGS)
     s = bs.solve_batch_sharded(gn, psf, bkg, flux=flux, betaParam=b0, divergence="beta", **bs.synth.STAMP_KWARGS)
     assert np.array_equal(s["x"], a.x) and np.array_equal(s["iters"], a.iters)
+    # device tensors in -> device tensors out, with the timing hook bench.py uses
+    import torch
+    dev = torch.device("cuda", 0)
+    t = {}
+    d = bs.solve_batch_sharded(torch.as_tensor(gn, device=dev), torch.as_tensor(psf, device=dev), torch.as_tensor(bkg, device=dev),
+                               flux=torch.as_tensor(flux, device=dev), betaParam=b0, divergence="beta", timing=t, **bs.synth.STAMP_KWARGS)
+    torch.cuda.synchronize()
+    assert np.array_equal(d["x"].cpu().numpy(), a.x) and np.array_equal(d["iters"].cpu().numpy(), a.iters)
+    assert t["solve"][0].elapsed_time(t["solve"][1]) > 0 and t["plan"]["ny"] == 32
+
+
+def test_adaptive_width_configurations_agree(bs, fixtures, golden):
+    """engine.auto_config trades cluster slots for per-image latency when a GPU holds few images (sharded runs); every
+    configuration it can select must give bit-identical results (same reduction order per image is NOT guaranteed across
+    cluster sizes, so: identical iteration counts, image <= 1e-9)."""
+    assert bs.engine.auto_config(256, 256, 320) == (0, 0) and bs.engine.auto_config(256, 256, 80) == (16, 128)
+    assert bs.engine.auto_config(256, 256, 40) == (0, 256) and bs.engine.auto_config(256, 256, 1) == (16, 256)
+    assert bs.engine.auto_config(32, 32, 5) == (0, 0) and bs.engine.auto_config(31, 31, 5) == (0, 0) and bs.engine.auto_config(8192, 8192, 1) == (0, 0)
+    names = ["tile00", "tile01", "tile07"]
+    ref = None
+    for cfg in ((0, 0), (16, 128), (0, 256), (16, 256)):
+        plan = bs.get_plan(256, 256, "float64", 0, *cfg)
+        out = []
+        for n in names:
+            gn = fixtures[f"tile{(int(n[4:]) // 5) * 5}/gn"]; bkg = fixtures[f"tile{(int(n[4:]) // 5) * 5}/bkg"]
+            r = bs.solve_batch(gn[None], fixtures["tile0/psf"], bkg[None], divergence="beta", flux=[float(golden[n + "/flux_in"])],
+                               betaParam=float(golden[n + "/beta0"]), plan=plan, **bs.synth.TILE_KWARGS)
+            assert int(r.iters[0]) == int(golden[n + "/iters"]), (cfg, n)
+            out.append(r.x[0])
+        if ref is None:
+            ref = out
+        for a_, b_ in zip(ref, out):
+            assert np.abs(a_ - b_).max() <= 1e-9 * np.abs(a_).max()
 
 
 @pytest.mark.parametrize("shape", [(64, 256), (128, 32)])

@@ -73,3 +73,26 @@ def test_oracle_error_behaviour(fixtures):
         orc.solve(gn, psf * 1.01, np.float64(1.0), MAXIT=2)
     with pytest.raises(ValueError, match="errflag"):
         orc.solve(gn, psf, np.float64(1.0), MAXIT=2, errflag=True)
+
+
+@pytest.mark.parametrize("shape,kshape", [((31, 31), (31, 31)), ((32, 32), (9, 9)), ((40, 37), (7, 11)), ((37, 40), (8, 8)),
+                                           ((64, 48), (10, 7)), ((33, 33), (32, 32))])
+def test_padded_operator_against_direct_space_convolution(shape, kshape):
+    """Independent check of oracle.PaddedPsf (the restatement of astropy's convolve_fft for sgp.py:138,157, whose parity
+    stays UNPINNED because astropy cannot be run here): for finite input, boundary='fill' with fill_value 0 and a
+    normalised kernel is the plain zero-fill 'same' convolution with the kernel origin at index n_k // 2, and the
+    "adjoint" of the reference is the same with the kernel psf.conj().T.  The comparison uses a DIRECT-SPACE convolution
+    (scipy.signal.convolve2d, no FFT), on odd and even image and kernel sizes."""
+    from scipy.signal import convolve2d
+    rng = np.random.default_rng(shape[0] * 100 + kshape[1])
+    x = rng.uniform(0.0, 100.0, shape)
+    k = rng.random(kshape) ** 3
+    k /= 7.3                                              # not normalised: convolve_fft(normalize_kernel=True) divides by the sum
+    op = orc.PaddedPsf(k, shape)
+    for kern, apply in ((k, op.forward), (k.conj().T, op.adjoint)):
+        kn = kern / kern.sum()
+        full = convolve2d(x, kn, mode="full", boundary="fill", fillvalue=0.0)
+        oy, ox = kern.shape[0] // 2, kern.shape[1] // 2
+        ref = full[oy:oy + shape[0], ox:ox + shape[1]]
+        got = apply(x.ravel()).reshape(shape)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()

@@ -1,4 +1,6 @@
-"""torchrun --nproc-per-node 2 tools/two_gpu_check.py : the sharded front end on two GPUs equals the single-GPU batch."""
+"""torchrun --nproc-per-node N tools/two_gpu_check.py : the sharded front end on N GPUs equals the single-GPU batch
+(numpy inputs and device tensors; stamps with per-image PSFs and tiles with a shared PSF / 2-D background; a batch smaller
+than the world size, i.e. empty shards)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,13 +11,27 @@ import beta_sgp_b200 as bs
 
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+world = dist.get_world_size()
 st = bs.synth.star_stamps(37, 32, seed=5)
 kw = dict(bs.synth.STAMP_KWARGS)
+ref = bs.sgp_betaDiv_batch(st["gn"], st["psf"], st["bkg"], flux=st["flux"], betaParam=st["beta0"], device=local, **kw)
 full = bs.solve_batch_sharded(st["gn"], st["psf"], st["bkg"], flux=st["flux"], betaParam=st["beta0"], divergence="beta", **kw)
+assert np.array_equal(full["x"], ref.x) and np.array_equal(full["iters"], ref.iters) and np.array_equal(full["discr"], ref.discr)
+t = {k: torch.as_tensor(st[k], device=dev) for k in ("gn", "psf", "bkg", "flux")}
+fd = bs.solve_batch_sharded(t["gn"], t["psf"], t["bkg"], flux=t["flux"], betaParam=st["beta0"], divergence="beta", **kw)
+assert np.array_equal(fd["x"].cpu().numpy(), ref.x) and np.array_equal(fd["iters"].cpu().numpy(), ref.iters)
+one = bs.solve_batch_sharded(st["gn"][:1], st["psf"][:1], st["bkg"][:1], flux=st["flux"][:1], betaParam=st["beta0"][:1], divergence="beta", **kw)
+assert np.array_equal(one["x"], ref.x[:1]) and one["iters"].shape == (1,)
+tl = bs.synth.field_tiles(size=512, tile=256, seed=3, n_beta=5)
+tk = dict(bs.synth.TILE_KWARGS)
+rt = bs.sgp_betaDiv_batch(tl["gn"], tl["psf"], tl["bkg"], flux=tl["flux"], betaParam=tl["beta0"], device=local, **tk)
+tt = {k: torch.as_tensor(tl[k], device=dev) for k in ("gn", "psf", "bkg", "flux")}
+ft = bs.solve_batch_sharded(tt["gn"], tt["psf"], tt["bkg"], flux=tt["flux"], betaParam=tl["beta0"], divergence="beta", **tk)
+assert np.array_equal(ft["iters"].cpu().numpy(), rt.iters)
+assert np.abs(ft["x"].cpu().numpy() - rt.x).max() <= 1e-9 * np.abs(rt.x).max()        # another CTA width per rank: same iterations, rounding-level image
 if dist.get_rank() == 0:
-    ref = bs.sgp_betaDiv_batch(st["gn"], st["psf"], st["bkg"], flux=st["flux"], betaParam=st["beta0"], device=local, **kw)
-    assert np.array_equal(full["x"], ref.x) and np.array_equal(full["iters"], ref.iters)
-    print("two-GPU sharded solve == single-GPU batch for", len(st["gn"]), "stamps; iters", full["iters"][:8])
+    print(f"{world}-GPU sharded solve == single-GPU batch: {len(st['gn'])} stamps (numpy, device tensors), 1 stamp (empty shards), {len(tl['gn'])} tiles; iters", full["iters"][:8])
 dist.barrier()
 dist.destroy_process_group()
