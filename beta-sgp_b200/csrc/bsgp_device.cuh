@@ -47,6 +47,8 @@ struct DeviceCtx {
     int tid, nt, rank, G;
     SharedCtl* sh;
     int parity;        // bit 0: inbox half in use; bits 1, 2: phase of mbar[0], mbar[1]
+    void* wst;         // this warp's copy of the solver's controller state (shared memory), see CtlState in bsgp_solver.cuh
+    template <class S> __device__ __forceinline__ S* ctl() const { return reinterpret_cast<S*>(wst); }
 
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void cluster_sync() {
@@ -132,7 +134,7 @@ __device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
     DeviceCtx c;
     c.tid = threadIdx.x; c.nt = blockDim.x; c.G = G;
     c.rank = (G > 1) ? (int)cg::this_cluster().block_rank() : 0;
-    c.sh = sh; c.parity = 0;
+    c.sh = sh; c.parity = 0; c.wst = nullptr;
     init_ctx_barriers(c);
     return c;
 }
@@ -151,6 +153,8 @@ struct GridCtx {
     SharedCtl* sh;
     double* gpart;      // [2][G][kMaxK]
     int parity;
+    void* wst;          // this warp's copy of the controller state (shared memory)
+    template <class S> __device__ __forceinline__ S* ctl() const { return reinterpret_cast<S*>(wst); }
 
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void cluster_sync() { cg::this_grid().sync(); }
@@ -195,7 +199,7 @@ struct GridCtx {
 __device__ __forceinline__ GridCtx make_grid_ctx(SharedCtl* sh, double* gpart) {
     GridCtx c;
     c.tid = threadIdx.x; c.nt = blockDim.x; c.G = gridDim.x; c.rank = blockIdx.x;
-    c.sh = sh; c.gpart = gpart; c.parity = 0;
+    c.sh = sh; c.gpart = gpart; c.parity = 0; c.wst = nullptr;
     return c;
 }
 
@@ -240,6 +244,8 @@ __device__ __forceinline__ int next_item(DeviceCtx& ctx, int* queue, const int* 
 // dynamic shared memory layout of the persistent kernels (byte offsets, computed by the host)
 struct SmemPlan {
     unsigned off_state;     // ImgState<T>
+    unsigned off_ctl;       // CtlState<T>, one copy per warp (stride ctl_stride bytes)
+    unsigned ctl_stride;
     unsigned off_twx;       // twiddles of the row transforms (if tw_smem)
     unsigned off_twy;       // twiddles of the column transforms (if tw_smem; may equal off_twx)
     unsigned off_ppx;       // padded-position table of the row transforms (nx x u16)

@@ -454,6 +454,8 @@ template <typename T> static int plan_setup_frame(bsgp_plan* p) {
     SmemPlan sp;
     size_t off = up128(sizeof(SharedCtl));
     sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
+    sp.ctl_stride = (unsigned)((sizeof(CtlState<T>) + 15) & ~(size_t)15);
+    sp.off_ctl = (unsigned)off; off = up128(off + (size_t)(p->threads / 32) * sp.ctl_stride);
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
     sp.tw_smem = tw_bytes <= 16384 ? 1 : 2;             // long transforms: two-level tables (64 + n/64 entries)
     sp.off_twx = sp.off_twy = (unsigned)off;
@@ -536,6 +538,8 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     SmemPlan sp;
     size_t off = up128(sizeof(SharedCtl));
     sp.off_state = (unsigned)off; off = up128(off + sizeof(ImgState<T>));
+    sp.ctl_stride = (unsigned)((sizeof(CtlState<T>) + 15) & ~(size_t)15);
+    sp.off_ctl = (unsigned)off; off = up128(off + (size_t)(threads / 32) * sp.ctl_stride);
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
     sp.tw_smem = tw_bytes <= 16384 ? 1 : 0;             // cluster mode: full tables in shared memory, or global
     sp.off_twx = (unsigned)off;

@@ -23,6 +23,7 @@ template <typename T, int NT, int MINB, bool MK>
 __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
     unsigned char* smem = dyn_smem();
     DeviceCtx ctx = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
+    ctx.wst = smem + sp.off_ctl + (threadIdx.x >> 5) * sp.ctl_stride;
     ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);
     const int cluster_id = blockIdx.x / a.g.G;
     const size_t npix = (size_t)a.g.ny * a.g.nx;
@@ -71,6 +72,7 @@ template <typename T, bool MK>
 __global__ void __launch_bounds__(512, 1) bsgp_frame_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride, double* gpart) {
     unsigned char* smem = dyn_smem();
     GridCtx ctx = make_grid_ctx(reinterpret_cast<SharedCtl*>(smem), gpart);
+    ctx.wst = smem + sp.off_ctl + (threadIdx.x >> 5) * sp.ctl_stride;
     ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);
     const size_t npix = (size_t)a.g.ny * a.g.nx;
     const size_t nslab = (size_t)a.g.rows_per_cta * a.g.nx;

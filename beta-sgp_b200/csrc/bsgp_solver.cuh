@@ -57,7 +57,7 @@ template <typename T> struct SolveArgs {
 template <typename T> struct ImgState {
     T* gn; T* bkg; T* x; T* g; T* xtf; T* d; T* dtf; T* t1;
     const T* gn_raw; const T* bkg_raw; const T* x0_raw; const T* truth; T* x_out;
-    const cplx<T>* twx; const cplx<T>* twy; cplx<T>* spec; cplx<T>* tf;
+    const cplx<T>* twx; const cplx<T>* twy; cplx<T>* spec; cplx<T>* tf; cplx<T>* tf_at;
     unsigned ws_off, ppx_off;        // FFT workspace and position table: byte offsets into dynamic shared memory
     unsigned twx_off, twy_off;       // twiddle tables in shared memory, or kNoSmem (then twx / twy are used)
     int tw_split;                    // the shared-memory tables are two-level (long transforms)
@@ -621,296 +621,381 @@ template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgSt
 // -------------------------------------------------------------------------------------------------
 // the controller
 // -------------------------------------------------------------------------------------------------
+// Controller scalars of one solve.  Every lane of every warp runs the scalar controller redundantly on bit-identical
+// all-reduced sums (uniform control flow, nothing is broadcast), but its state does not live in registers: each WARP
+// owns one copy of this block in shared memory (Ctx::ctl) and all of its lanes store the same values to it.  Nothing of
+// the controller is therefore alive in registers across the calls of the non-inlined phases, reductions and root-find
+// (round 1: ~100 live scalars, 260 M local-memory loads per launch that missed the carved-out L1), and those callees can
+// be real functions instead of 40 inlined copies (the kernel's main body shrank from 18.5 k to a few thousand
+// instructions).  A warp never reads another warp's copy, so no barrier orders the accesses; within a warp every lane
+// reads back what it, or a lane in lock step with it, has just written.
+template <typename T> struct CtlState {
+    double flux, tol, discr_coeff, npix_d, truth_sq, t_start, sum_raw;
+    double alpha, tau, lr, beta_p, s1, fv, x_low, x_upp, f_prev, lam, gd, f_ref;
+    double pre[3];                                   // sums of x(lambda) at lambda = 0, +1, -1 delivered by ph_trial_point
+    double alpha_hist[kMaxMem], f_hist[kMaxMem];     // Valpha / Fold (sgp.py:214-215)
+    DivK<T> dk;
+    T al, lam_pending, lam_proj;
+    int status, total_evals, total_trials, iter, trials, evals, flags;
+    int have_pre, s1_valid, X_is_ones, keep_going, pending;
+};
+
+// all-reduce of K doubles as a real function (the execution context travels by value, its parity comes back)
+template <int K> struct ArOut { double v[K]; int parity; };
+template <int OP, int K, class Ctx> BSGP_NOINLINE ArOut<K> ar_call(Ctx ctx, ArOut<K> io) {
+    ctx.allreduce(OP, io.v, K);
+    io.parity = ctx.parity;
+    return io;
+}
+template <int OP, int K, class Ctx> BSGP_DEV void allreduce_fn(Ctx& ctx, double* v) {
+    ArOut<K> io;
+#pragma unroll
+    for (int j = 0; j < K; ++j) io.v[j] = v[j];
+    io.parity = 0;
+    io = ar_call<OP, K>(ctx, io);
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] = io.v[j];
+    ctx.parity = io.parity;
+}
+
+// The projection root-find of one call (initial projection or one iteration), as a real function: the residual
+// r(lambda) = sum_i x_i(lambda) - flux comes from the fused sums of ph_trial_point where it can, else from one pass.
+struct RfOut { ProjResult pr; int parity; };
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE RfOut rootfind_call(Ctx ctx, const ImgState<T>* S, const CtlState<T>* W, int max_projs) {
+    const double flux = W->flux;
+    const bool have_pre = W->have_pre != 0;
+    const double p0 = W->pre[0], p1 = W->pre[1], p2 = W->pre[2];
+    auto proj_eval = [&](double lam) -> double {
+        if (have_pre) {
+            if (lam == 0.0) return p0 - flux;
+            if (lam == 1.0) return p1 - flux;
+            if (lam == -1.0) return p2 - flux;
+        }
+        double s = ph_proj_eval<T, MK>(ctx, S, (T)lam);
+        allreduce_fn<0, 1>(ctx, &s);
+        return s - flux;
+    };
+    RfOut out;
+    out.pr = flux_rootfind(proj_eval, flux, max_projs);
+    out.parity = ctx.parity;
+    return out;
+}
+
+// Barzilai-Borwein steps and their alternation, learning-rate schedule, bookkeeping and stop rules of one iteration
+// (sgp.py:366-425 / 818-882).  bb: the seven all-reduced sums of ph_ri_bb.  Returns the value compared with tol.
+template <typename T> BSGP_NOINLINE double ctl_finish_iteration(const bsgp_params* Pp, CtlState<T>* W, R7 bbr) {
+    const bsgp_params& P = *Pp;
+    const double* bb = bbr.v;
+    const int MA = P.m_alpha;
+    const double alpha_prev = W->alpha;
+    const double bk = bb[0], ck = bb[1];
+    double a1, a2;
+    if (bk <= 0.0) a1 = py_min(nmul(10.0, alpha_prev), P.alpha_max);
+    else a1 = py_min(P.alpha_max, py_max(P.alpha_min, bb[2] / bk));
+    if (ck <= 0.0) a2 = py_min(nmul(10.0, alpha_prev), P.alpha_max);
+    else a2 = py_min(P.alpha_max, py_max(P.alpha_min, ck / bb[3]));
+    W->alpha_hist[MA - 1] = a2;
+    double amin = W->alpha_hist[0];
+    for (int k = 1; k < MA; ++k) amin = py_min(amin, W->alpha_hist[k]);
+    const int iter = W->iter;
+    double tau = W->tau, alpha;
+    if (iter <= 20) alpha = amin;
+    else if (a2 / a1 < tau) { alpha = amin; tau = nmul(tau, 0.9); }
+    else { alpha = a1; tau = nmul(tau, 1.1); }
+    W->alpha = alpha; W->tau = tau;
+    if (P.divergence == BSGP_DIV_BETA && P.schedule_lr) W->lr = nmul(P.lr, exp(nmul(-P.lr_exp_param, (double)iter)));   // :842-844, epoch == iter
+    // ---- bookkeeping and stop rules (:390-425)
+    const int it1 = iter + 1;
+    W->iter = it1;
+    const double fv = W->fv;
+    double stop_val = 0.0;
+    int keep_going = 1;
+    if (P.stop_criterion == 2) {
+        stop_val = bb[4] / bb[5];
+        keep_going = stop_val > W->tol;
+    } else if (P.stop_criterion == 3) {
+        stop_val = (W->f_prev - fv) / fv;
+        keep_going = (stop_val > W->tol) && (stop_val >= 0.0);
+    } else if (P.stop_criterion == 4) {
+        stop_val = nmul(W->discr_coeff, fv);
+        keep_going = stop_val > W->tol;
+    }
+    if (it1 > P.maxit) keep_going = 0;
+    W->keep_going = keep_going;
+    return stop_val;
+}
+
 template <typename T, bool MK, class Ctx>
 BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* const* buf, cplx<T>* tf, cplx<T>* tf_adj, int img) {
     const bsgp_params& P = a.p;
-    const int nslab = a.g.rows_per_cta * a.g.nx;
-    const size_t npix = (size_t)a.g.ny * a.g.nx;
+    CtlState<T>* W = ctx.template ctl<CtlState<T>>();
     constexpr bool masked = MK;                                          // zero-padded operator: the image is a window of the grid
-    const double npix_d = masked ? (double)(P.region[1] - P.region[0]) * (double)(P.region[3] - P.region[2]) : (double)npix;
-    // A^T: conj(TF) of the same PSF (sgp.py:110), or the spectrum of a second kernel, psf.conj().T (sgp.py:157)
-    cplx<T>* tf_at = P.adjoint_second_psf ? tf_adj : tf;
-    const int mode_at = P.adjoint_second_psf ? CONV_TF : CONV_CTF;
-    const size_t goff = (size_t)img * npix + (size_t)ctx.rank * nslab;
-    const size_t toff = (size_t)img * (P.maxit + 1);
     const bool leader = (ctx.rank == 0 && ctx.tid == 0);
     const bool pflag = P.proj_type == 1;
     const bool is_beta = P.divergence == BSGP_DIV_BETA;
-    const bool bkg_img = a.bkg_is_image != 0;
     const bool want_err = P.errflag && a.obj != nullptr && a.err != nullptr;
-    const T bkg_raw_s = bkg_img ? (T)0 : a.bkg[img];
-    const double t_start = ctx.now();
+    const size_t toff = (size_t)img * (P.maxit + 1);
 
     ctx.sync();                      // the previous image's last phase may still be reading S
-    if (ctx.tid == 0) {
-        S->gn = buf[B_GN]; S->bkg = buf[B_BKG]; S->x = buf[B_X]; S->g = buf[B_G];
-        S->xtf = buf[B_XTF]; S->d = buf[B_D]; S->dtf = buf[B_DTF]; S->t1 = buf[B_T1];
-        S->gn_raw = a.gn + goff;
-        S->bkg_raw = bkg_img ? a.bkg + goff : a.gn + goff;             // never dereferenced when !bkg_img
-        S->x0_raw = (P.init_recon == 1) ? a.x0 + goff : a.gn + goff;
-        S->truth = want_err ? a.obj + goff : a.gn + goff;
-        S->x_out = a.x_out + goff;
-        S->tf = tf;
-        S->nslab = nslab; S->bkg_img = bkg_img; S->init_recon = P.init_recon; S->has_cap = P.has_sat != 0;
-        S->pflag = pflag; S->want_err = want_err; S->stop2 = (P.stop_criterion == 2);
-        S->bkg_raw_s = bkg_raw_s;
-        S->masked = masked; S->reg[0] = P.region[0]; S->reg[1] = P.region[1]; S->reg[2] = P.region[2]; S->reg[3] = P.region[3];
-        S->div_a = masked ? (T)P.div_a : (T)1; S->div_at = masked ? (T)P.div_at : (T)1;
+    {
+        const int nslab = a.g.rows_per_cta * a.g.nx;
+        const size_t npix = (size_t)a.g.ny * a.g.nx;
+        const size_t goff = (size_t)img * npix + (size_t)ctx.rank * nslab;
+        const bool bkg_img = a.bkg_is_image != 0;
+        const T bkg_raw_s = bkg_img ? (T)0 : a.bkg[img];
+        if (ctx.tid == 0) {
+            S->gn = buf[B_GN]; S->bkg = buf[B_BKG]; S->x = buf[B_X]; S->g = buf[B_G];
+            S->xtf = buf[B_XTF]; S->d = buf[B_D]; S->dtf = buf[B_DTF]; S->t1 = buf[B_T1];
+            S->gn_raw = a.gn + goff;
+            S->bkg_raw = bkg_img ? a.bkg + goff : a.gn + goff;             // never dereferenced when !bkg_img
+            S->x0_raw = (P.init_recon == 1) ? a.x0 + goff : a.gn + goff;
+            S->truth = want_err ? a.obj + goff : a.gn + goff;
+            S->x_out = a.x_out + goff;
+            S->tf = tf;
+            // A^T: conj(TF) of the same PSF (sgp.py:110), or the spectrum of a second kernel, psf.conj().T (sgp.py:157)
+            S->tf_at = P.adjoint_second_psf ? tf_adj : tf;
+            S->nslab = nslab; S->bkg_img = bkg_img; S->init_recon = P.init_recon; S->has_cap = P.has_sat != 0;
+            S->pflag = pflag; S->want_err = want_err; S->stop2 = (P.stop_criterion == 2);
+            S->bkg_raw_s = bkg_raw_s;
+            S->masked = masked; S->reg[0] = P.region[0]; S->reg[1] = P.region[1]; S->reg[2] = P.region[2]; S->reg[3] = P.region[3];
+            S->div_a = masked ? (T)P.div_a : (T)1; S->div_at = masked ? (T)P.div_at : (T)1;
+        }
+        W->npix_d = masked ? (double)(P.region[1] - P.region[0]) * (double)(P.region[3] - P.region[2]) : (double)npix;
+        W->t_start = ctx.now();
     }
+    const int mode_at = P.adjoint_second_psf ? CONV_TF : CONV_CTF;
 
     // ------------------------------------------------------------------ setup (sgp.py:166-217)
-    double v3[3];
-    const R3 st = ph_stats<T, MK>(ctx, S);
-    v3[0] = st.a; v3[1] = st.b;
-    double mx = st.c;
-    ctx.allreduce_sum(v3, 2);
-    ctx.allreduce_max(mx);
-    const double sum_raw = v3[0], sum_gb_raw = v3[1];
-    const T scaling = P.scale_data ? (T)mx : (T)1;
-    const T bkg_s = ndiv(bkg_raw_s, scaling);
-    if (ctx.tid == 0) { S->scaling = scaling; S->bkg_s = bkg_s; }
-
-    double vmin = ph_scale_gn<T, MK>(ctx, S);
-    ctx.allreduce_min(vmin);
-    const T eps = Eps<T>::v();
-    const double flux_in = P.has_flux ? a.flux[img] : 0.0;
-    const bool has_cap = P.has_sat != 0;
-    if (ctx.tid == 0) {
-        S->null_fill = nmul(nmul((T)vmin, eps), eps);
-        S->x_const = ndiv(nmul((T)ndiv(P.has_flux ? flux_in : sum_gb_raw, npix_d), (T)1), scaling);
-        S->cap = has_cap ? nsub(ndiv((T)P.ccd_sat_level, scaling), eps) : (T)0;
-        S->xlo = (T)0; S->xhi = (T)0;
+    {
+        const R3 st = ph_stats<T, MK>(ctx, S);
+        double v2[2] = {st.a, st.b};
+        double mx = st.c;
+        allreduce_fn<0, 2>(ctx, v2);
+        allreduce_fn<2, 1>(ctx, &mx);
+        const T scaling = P.scale_data ? (T)mx : (T)1;
+        const T bkg_s = ndiv(S->bkg_raw_s, scaling);
+        if (ctx.tid == 0) { S->scaling = scaling; S->bkg_s = bkg_s; }
+        W->sum_raw = v2[0];
+        W->flux = v2[1];                                                 // sum(gn - bkg) of the raw data, until ph_init refines it
     }
-    v3[0] = ph_init<T, MK>(ctx, S);
-    ctx.allreduce_sum(v3, 1);
-    const double flux = P.has_flux ? ndiv(flux_in, (double)scaling) : v3[0];
-
-    double tol = 0.0;                                                   // sgp.py:185-190, 291-294
-    if (P.stop_criterion == 2 || P.stop_criterion == 3) tol = P.tol_convergence;
-    else if (P.stop_criterion == 4) tol = 1.0 + 1.0 / (sum_raw / npix_d);
-    if (P.verbose && P.stop_criterion == 2) tol = nmul(tol, tol);
-    const double discr_coeff = nmul(2.0 / npix_d, (double)scaling);
-
-    int status = BSGP_ST_OK;
-    int total_evals = 0, total_trials = 0;
-    if (pflag && !(flux > 0.0 && is_finite(flux))) status = BSGP_ST_BAD_FLUX;
-
-    bool have_pre = false;            // sums of x(lambda) at lambda = 0, +1, -1 delivered by ph_trial_point
-    double pre[3] = {0.0, 0.0, 0.0};
-    auto proj_eval = [&](double lam) -> double {
-        if (have_pre) {
-            if (lam == 0.0) return pre[0] - flux;
-            if (lam == 1.0) return pre[1] - flux;
-            if (lam == -1.0) return pre[2] - flux;
+    {
+        double vmin = ph_scale_gn<T, MK>(ctx, S);
+        allreduce_fn<1, 1>(ctx, &vmin);
+        const T eps = Eps<T>::v();
+        const T scaling = S->scaling;
+        const double flux_in = P.has_flux ? a.flux[img] : 0.0;
+        if (ctx.tid == 0) {
+            S->null_fill = nmul(nmul((T)vmin, eps), eps);
+            S->x_const = ndiv(nmul((T)ndiv(P.has_flux ? flux_in : W->flux, W->npix_d), (T)1), scaling);
+            S->cap = (P.has_sat != 0) ? nsub(ndiv((T)P.ccd_sat_level, scaling), eps) : (T)0;
+            S->xlo = (T)0; S->xhi = (T)0;
         }
-        double s = ph_proj_eval<T, MK>(ctx, S, (T)lam);
-        ctx.allreduce_sum(&s, 1);
-        return s - flux;
-    };
+        double v1 = ph_init<T, MK>(ctx, S);
+        allreduce_fn<0, 1>(ctx, &v1);
+        W->flux = P.has_flux ? ndiv(flux_in, (double)scaling) : v1;
+
+        double tol = 0.0;                                                   // sgp.py:185-190, 291-294
+        if (P.stop_criterion == 2 || P.stop_criterion == 3) tol = P.tol_convergence;
+        else if (P.stop_criterion == 4) tol = 1.0 + 1.0 / (W->sum_raw / W->npix_d);
+        if (P.verbose && P.stop_criterion == 2) tol = nmul(tol, tol);
+        W->tol = tol;
+        W->discr_coeff = nmul(2.0 / W->npix_d, (double)scaling);
+    }
+    W->status = BSGP_ST_OK;
+    W->total_evals = 0; W->total_trials = 0;
+    W->have_pre = 0;
+    if (pflag && !(W->flux > 0.0 && is_finite(W->flux))) W->status = BSGP_ST_BAD_FLUX;
 
     // ------------------------------------------------------------------ initial projection (:248-253)
-    if (status == BSGP_ST_OK) {
+    if (W->status == BSGP_ST_OK) {
         ph_proj_init_load<T>(ctx, S);
         if (pflag) {
-            const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
-            total_evals += pr.evals;
-            if (pr.status != PROJ_OK) status = BSGP_ST_PROJ_NO_BRACKET;
+            const RfOut rf = rootfind_call<T, MK>(ctx, S, W, P.max_projs);
+            ctx.parity = rf.parity;
+            const ProjResult pr = rf.pr;
+            W->total_evals += pr.evals;
+            if (pr.status != PROJ_OK) W->status = BSGP_ST_PROJ_NO_BRACKET;
             ph_proj_init_store<T, MK>(ctx, S, (T)pr.lambda);
         }
     }
 
-    double truth_sq = 1.0;
-    if (want_err && status == BSGP_ST_OK) {                             // :240-244, 255-257
+    W->truth_sq = 1.0;
+    if (want_err && W->status == BSGP_ST_OK) {                          // :240-244, 255-257
         const R2 e = ph_err0<T, MK>(ctx, S);
         double e2[2] = {e.a, e.b};
-        ctx.allreduce_sum(e2, 2);
-        truth_sq = e2[1];
-        if (leader) a.err[(size_t)img * (P.maxit + 2)] = sqrt(e2[0] / truth_sq);
+        allreduce_fn<0, 2>(ctx, e2);
+        W->truth_sq = e2[1];
+        if (leader) a.err[(size_t)img * (P.maxit + 2)] = sqrt(e2[0] / e2[1]);
     }
 
-    double beta_p = is_beta ? a.beta0[img] : 1.0;
-    DivK<T> dk = make_divk<T>(P.divergence, beta_p);
-    double s1 = 0.0;          // sum k*gn^beta for the current beta
-    bool s1_valid = false;
-    double fv = 0.0, x_low = 0.0, x_upp = 0.0;
-    double acc[4];
+    W->beta_p = is_beta ? a.beta0[img] : 1.0;
+    W->dk = make_divk<T>(P.divergence, W->beta_p);
+    W->s1 = 0.0;              // sum k*gn^beta for the current beta
+    W->s1_valid = 0;
+    W->fv = 0.0; W->x_low = 0.0; W->x_upp = 0.0;
 
-    if (status == BSGP_ST_OK) {
+    if (W->status == BSGP_ST_OK) {
         // ---------------------------------------------------------------- x_tf = A(x), objective (:260-265)
         ph_rf_copy<T>(ctx, S, 0);
-        conv_middle<T>(ctx, S, tf, CONV_TF);
+        conv_middle<T>(ctx, S, S->tf, CONV_TF);
+        double acc[3];
         {
-            const R3 o = ph_ri_obj0<T, MK>(ctx, S, dk, !s1_valid);
+            const R3 o = ph_ri_obj0<T, MK>(ctx, S, W->dk, !W->s1_valid);
             acc[0] = o.a; acc[1] = o.b; acc[2] = o.c;
         }
-        ctx.allreduce_sum(acc, 3);
-        if (dk.kind == 1) { s1 = acc[0]; s1_valid = true; }
-        fv = objective_value(dk, acc, s1, flux, npix_d);
+        allreduce_fn<0, 3>(ctx, acc);
+        if (W->dk.kind == 1) { W->s1 = acc[0]; W->s1_valid = 1; }
+        W->fv = objective_value(W->dk, acc, W->s1, W->flux, W->npix_d);
         // ---------------------------------------------------------------- gradient
-        ph_rf_grad<T, MK>(ctx, S, dk.kind, (T)0, F_FIRST);
-        conv_middle<T>(ctx, S, tf_at, mode_at);
-        ph_ri_grad0<T, MK>(ctx, S, dk.kind);
+        ph_rf_grad<T, MK>(ctx, S, W->dk.kind, (T)0, F_FIRST);
+        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        ph_ri_grad0<T, MK>(ctx, S, W->dk.kind);
         // ---------------------------------------------------------------- scaling-matrix bounds (:268-273)
         ph_rf_copy<T>(ctx, S, 1);
-        conv_middle<T>(ctx, S, tf_at, mode_at);
-        const R2 lh = ph_ri_bounds<T, MK>(ctx, S, flux);
+        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        const R2 lh = ph_ri_bounds<T, MK>(ctx, S, W->flux);
         double lo = lh.a, hi = lh.b;
-        ctx.allreduce_min(lo);
-        ctx.allreduce_max(hi);
-        if (!(lo < INFINITY)) status = BSGP_ST_EMPTY_BOUNDS;
-        x_low = lo; x_upp = hi;
+        allreduce_fn<1, 1>(ctx, &lo);
+        allreduce_fn<2, 1>(ctx, &hi);
+        if (!(lo < INFINITY)) W->status = BSGP_ST_EMPTY_BOUNDS;
+        double x_low = lo, x_upp = hi;
         if (x_upp / x_low < 50.0) { x_low = x_low / 10.0; x_upp = x_upp * 10.0; }
+        W->x_low = x_low; W->x_upp = x_upp;
         if (ctx.tid == 0) { S->xlo = (T)x_low; S->xhi = (T)x_upp; }
     }
 
     if (leader) {
-        a.discr[toff] = nmul(discr_coeff, fv);
+        a.discr[toff] = nmul(W->discr_coeff, W->fv);
         a.times[toff] = 0.0;
         if (a.stop_value) a.stop_value[toff] = 0.0;
     }
 
     // ------------------------------------------------------------------ main loop (sgp.py:302-425)
-    double alpha = P.alpha, tau = P.tau, lr = P.lr;
-    const int M = P.m, MA = P.m_alpha;
-    double alpha_hist[kMaxMem], f_hist[kMaxMem];      // Valpha / Fold (sgp.py:214-215); dynamically indexed -> local memory
-    for (int k = 0; k < MA; ++k) alpha_hist[k] = P.alpha_max;
-    for (int k = 0; k < M; ++k) f_hist[k] = -1e30;
-    bool X_is_ones = (P.init_recon == 0);
-    int iter = 1;
-    bool keep_going = (status == BSGP_ST_OK);
+    W->alpha = P.alpha; W->tau = P.tau; W->lr = P.lr;
+    {
+        const int M = P.m, MA = P.m_alpha;
+        for (int k = 0; k < MA; ++k) W->alpha_hist[k] = P.alpha_max;
+        for (int k = 0; k < M; ++k) W->f_hist[k] = -1e30;
+    }
+    W->X_is_ones = (P.init_recon == 0);
+    W->iter = 1;
+    W->keep_going = (W->status == BSGP_ST_OK);
     // The accepted step x <- x + lam*d is applied lazily at the start of the NEXT iteration, so when
     // the loop stops x still holds the previous iterate, which is what the reference returns (:424-425).
-    bool pending = false;
-    T lam_pending = (T)0;
+    W->pending = 0;
+    W->lam_pending = (T)0;
 
-    while (keep_going) {
+    while (W->keep_going) {
         // history shift (:306-308)
-        for (int k = 0; k < MA - 1; ++k) alpha_hist[k] = alpha_hist[k + 1];
-        for (int k = 0; k < M - 1; ++k) f_hist[k] = f_hist[k + 1];
-        f_hist[M - 1] = fv;
-        const double f_prev = fv;
+        {
+            const int M = P.m, MA = P.m_alpha;
+            for (int k = 0; k < MA - 1; ++k) W->alpha_hist[k] = W->alpha_hist[k + 1];
+            for (int k = 0; k < M - 1; ++k) W->f_hist[k] = W->f_hist[k + 1];
+            W->f_hist[M - 1] = W->fv;
+            W->f_prev = W->fv;
+        }
 
         // ---- trial point y = x - alpha X g, projection (:311-318)
-        const T al = (T)alpha;
-        int flags = (pending ? F_PENDING : 0) | (X_is_ones ? F_XONES : 0);
-        int evals = 0;
-        T lam_proj = (T)0;
+        W->al = (T)W->alpha;
+        W->flags = (W->pending ? F_PENDING : 0) | (W->X_is_ones ? F_XONES : 0);
+        W->evals = 0;
+        W->lam_proj = (T)0;
         if (pflag) {
             {
-                const R3 t = ph_trial_point<T, MK>(ctx, S, al, lam_pending, flags);
-                pre[0] = t.a; pre[1] = t.b; pre[2] = t.c;
-                ctx.allreduce_sum(pre, 3);
-                have_pre = true;
+                const R3 t = ph_trial_point<T, MK>(ctx, S, W->al, W->lam_pending, W->flags);
+                double pre[3] = {t.a, t.b, t.c};
+                allreduce_fn<0, 3>(ctx, pre);
+                W->pre[0] = pre[0]; W->pre[1] = pre[1]; W->pre[2] = pre[2];
+                W->have_pre = 1;
             }
-            pending = false;
-            flags &= ~F_PENDING;
-            const ProjResult pr = flux_rootfind(proj_eval, flux, P.max_projs);
-            evals = pr.evals;
-            total_evals += evals;
-            if (pr.status != PROJ_OK) { status = BSGP_ST_PROJ_NO_BRACKET; break; }
-            lam_proj = (T)pr.lambda;
+            W->pending = 0;
+            W->flags &= ~F_PENDING;
+            const RfOut rf = rootfind_call<T, MK>(ctx, S, W, P.max_projs);
+            ctx.parity = rf.parity;
+            const ProjResult pr = rf.pr;
+            W->evals = pr.evals;
+            W->total_evals += pr.evals;
+            if (pr.status != PROJ_OK) { W->status = BSGP_ST_PROJ_NO_BRACKET; break; }
+            W->lam_proj = (T)pr.lambda;
         }
 
         // ---- d = y - x, gd = d.g, d_tf = A(d) with the first line-search trial fused (:318-334)
-        double sums[4];   // [0..2] objective terms, [3] gd
-        double lam = 1.0;
-        sums[3] = ph_rf_dir<T, MK>(ctx, S, al, lam_proj, lam_pending, flags);
-        pending = false;
-        conv_middle<T>(ctx, S, tf, CONV_TF);
         {
-            const R3 o = ph_ri_trial<T, MK>(ctx, S, dk, !s1_valid);
-            sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
-        }
-        ctx.allreduce_sum(sums, 4);
-        const double gd = sums[3];
-        if (dk.kind == 1 && !s1_valid) { s1 = sums[0]; s1_valid = true; }
-        fv = objective_value(dk, sums, s1, flux, npix_d);
-        double f_ref = f_hist[0];                                        // fr = max(Fold)
-        for (int k = 1; k < M; ++k) f_ref = py_max(f_ref, f_hist[k]);
-        int trials = 1;
-        // ---- backtracking (:328-349 / :776-800): accept iff fv <= fr + gamma*lam*gd or lam < 1e-12
-        while (!(fv <= nadd(f_ref, nmul(nmul(P.gamma, lam), gd)) || lam < 1e-12)) {
-            if (is_beta && P.adapt_beta && dk.kind == 1) {               // :798-800, den of the rejected trial
-                double db = ph_dbeta<T, MK>(ctx, S, (T)lam, dk.b);
-                ctx.allreduce_sum(&db, 1);
-                beta_p = nsub(beta_p, nmul(lr, db / npix_d));
-                dk = make_divk<T>(P.divergence, beta_p);
-                s1_valid = false;
+            double sums[4];   // [0..2] objective terms, [3] gd
+            sums[3] = ph_rf_dir<T, MK>(ctx, S, W->al, W->lam_proj, W->lam_pending, W->flags);
+            W->pending = 0;
+            conv_middle<T>(ctx, S, S->tf, CONV_TF);
+            {
+                const R3 o = ph_ri_trial<T, MK>(ctx, S, W->dk, !W->s1_valid);
+                sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             }
-            lam = nmul(lam, P.ls_beta);
-            ++trials;
-            const R3 o = ph_trial<T, MK>(ctx, S, (T)lam, dk, !s1_valid);
-            sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
-            ctx.allreduce_sum(sums, 3);
-            if (dk.kind == 1 && !s1_valid) { s1 = sums[0]; s1_valid = true; }
-            fv = objective_value(dk, sums, s1, flux, npix_d);
+            allreduce_fn<0, 4>(ctx, sums);
+            W->gd = sums[3];
+            if (W->dk.kind == 1 && !W->s1_valid) { W->s1 = sums[0]; W->s1_valid = 1; }
+            W->fv = objective_value(W->dk, sums, W->s1, W->flux, W->npix_d);
+            const int M = P.m;
+            double f_ref = W->f_hist[0];                                     // fr = max(Fold)
+            for (int k = 1; k < M; ++k) f_ref = py_max(f_ref, W->f_hist[k]);
+            W->f_ref = f_ref;
         }
-        total_trials += trials;
+        W->lam = 1.0;
+        W->trials = 1;
+        // ---- backtracking (:328-349 / :776-800): accept iff fv <= fr + gamma*lam*gd or lam < 1e-12
+        while (!(W->fv <= nadd(W->f_ref, nmul(nmul(P.gamma, W->lam), W->gd)) || W->lam < 1e-12)) {
+            if (is_beta && P.adapt_beta && W->dk.kind == 1) {               // :798-800, den of the rejected trial
+                double db = ph_dbeta<T, MK>(ctx, S, (T)W->lam, W->dk.b);
+                allreduce_fn<0, 1>(ctx, &db);
+                W->beta_p = nsub(W->beta_p, nmul(W->lr, db / W->npix_d));
+                W->dk = make_divk<T>(P.divergence, W->beta_p);
+                W->s1_valid = 0;
+            }
+            W->lam = nmul(W->lam, P.ls_beta);
+            W->trials += 1;
+            double sums[3];
+            const R3 o = ph_trial<T, MK>(ctx, S, (T)W->lam, W->dk, !W->s1_valid);
+            sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
+            allreduce_fn<0, 3>(ctx, sums);
+            if (W->dk.kind == 1 && !W->s1_valid) { W->s1 = sums[0]; W->s1_valid = 1; }
+            W->fv = objective_value(W->dk, sums, W->s1, W->flux, W->npix_d);
+        }
+        W->total_trials += W->trials;
 
         // ---- accept: x_tf, new gradient through A^T, BB sums (:337-347, 355-365, 402); x itself is updated lazily
-        ph_rf_grad<T, MK>(ctx, S, dk.kind, (T)lam, 0);
-        conv_middle<T>(ctx, S, tf_at, mode_at);
-        R7 bbr = ph_ri_bb<T, MK>(ctx, S, (T)lam, dk.kind);
-        double* bb = bbr.v;
-        ctx.allreduce_sum(bb, 7);
-        X_is_ones = false;
+        ph_rf_grad<T, MK>(ctx, S, W->dk.kind, (T)W->lam, 0);
+        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        R7 bbr = ph_ri_bb<T, MK>(ctx, S, (T)W->lam, W->dk.kind);
+        allreduce_fn<0, 7>(ctx, bbr.v);
+        W->X_is_ones = 0;
 
-        // ---- Barzilai-Borwein steps and their alternation (:366-386)
-        const double bk = bb[0], ck = bb[1];
-        double a1, a2;
-        if (bk <= 0.0) a1 = py_min(nmul(10.0, alpha), P.alpha_max);
-        else a1 = py_min(P.alpha_max, py_max(P.alpha_min, bb[2] / bk));
-        if (ck <= 0.0) a2 = py_min(nmul(10.0, alpha), P.alpha_max);
-        else a2 = py_min(P.alpha_max, py_max(P.alpha_min, ck / bb[3]));
-        alpha_hist[MA - 1] = a2;
-        double amin = alpha_hist[0];
-        for (int k = 1; k < MA; ++k) amin = py_min(amin, alpha_hist[k]);
-        if (iter <= 20) alpha = amin;
-        else if (a2 / a1 < tau) { alpha = amin; tau = nmul(tau, 0.9); }
-        else { alpha = a1; tau = nmul(tau, 1.1); }
-
-        if (is_beta && P.schedule_lr) lr = nmul(P.lr, exp(nmul(-P.lr_exp_param, (double)iter)));   // :842-844, epoch == iter
-
-        // ---- bookkeeping and stop rules (:390-425)
-        ++iter;
-        double stop_val = 0.0;
-        if (P.stop_criterion == 2) {
-            stop_val = bb[4] / bb[5];
-            keep_going = stop_val > tol;
-        } else if (P.stop_criterion == 3) {
-            stop_val = (f_prev - fv) / fv;
-            keep_going = (stop_val > tol) && (stop_val >= 0.0);
-        } else if (P.stop_criterion == 4) {
-            stop_val = nmul(discr_coeff, fv);
-            keep_going = stop_val > tol;
-        }
-        if (iter > P.maxit) keep_going = false;
+        // ---- Barzilai-Borwein steps, lr schedule, bookkeeping and stop rules (:366-425)
+        const double stop_val = ctl_finish_iteration<T>(&a.p, W, bbr);
         if (leader) {
+            const int iter = W->iter;
             const size_t o = toff + (size_t)(iter - 1);
-            a.times[o] = ctx.now() - t_start;
-            a.discr[o] = nmul(discr_coeff, fv);
+            a.times[o] = ctx.now() - W->t_start;
+            a.discr[o] = nmul(W->discr_coeff, W->fv);
             if (a.stop_value) a.stop_value[o] = stop_val;
-            if (a.tr_alpha) a.tr_alpha[o] = alpha;
-            if (a.tr_lambda) a.tr_lambda[o] = lam;
-            if (a.tr_beta) a.tr_beta[o] = beta_p;
-            if (a.tr_trials) a.tr_trials[o] = trials;
-            if (a.tr_evals) a.tr_evals[o] = evals;
-            if (want_err && iter <= P.maxit + 1) a.err[(size_t)img * (P.maxit + 2) + iter] = sqrt(bb[6] / truth_sq);   // :394-396
+            if (a.tr_alpha) a.tr_alpha[o] = W->alpha;
+            if (a.tr_lambda) a.tr_lambda[o] = W->lam;
+            if (a.tr_beta) a.tr_beta[o] = W->beta_p;
+            if (a.tr_trials) a.tr_trials[o] = W->trials;
+            if (a.tr_evals) a.tr_evals[o] = W->evals;
+            if (want_err && iter <= P.maxit + 1) a.err[(size_t)img * (P.maxit + 2) + iter] = sqrt(bbr.v[6] / W->truth_sq);   // :394-396
         }
-        if (keep_going) { pending = true; lam_pending = (T)lam; }       // else: the previous iterate is returned (:424-425)
+        if (W->keep_going) { W->pending = 1; W->lam_pending = (T)W->lam; }       // else: the previous iterate is returned (:424-425)
     }
 
     // ------------------------------------------------------------------ epilogue (:427-438)
     ph_store_out<T>(ctx, S);
     if (leader) {
-        a.iters[img] = iter - 1;
-        a.status[img] = status;
-        if (a.beta_final) a.beta_final[img] = beta_p;
-        if (a.proj_evals) a.proj_evals[img] = total_evals;
-        if (a.ls_trials) a.ls_trials[img] = total_trials;
+        a.iters[img] = W->iter - 1;
+        a.status[img] = W->status;
+        if (a.beta_final) a.beta_final[img] = W->beta_p;
+        if (a.proj_evals) a.proj_evals[img] = W->total_evals;
+        if (a.ls_trials) a.ls_trials[img] = W->total_trials;
         if (a.scalars) {
             double* sc = a.scalars + (size_t)img * BSGP_NSCALARS;
-            sc[0] = (double)scaling; sc[1] = flux; sc[2] = x_low; sc[3] = x_upp; sc[4] = tol; sc[5] = fv; sc[6] = alpha; sc[7] = tau;
+            sc[0] = (double)S->scaling; sc[1] = W->flux; sc[2] = W->x_low; sc[3] = W->x_upp; sc[4] = W->tol; sc[5] = W->fv; sc[6] = W->alpha; sc[7] = W->tau;
         }
     }
 }

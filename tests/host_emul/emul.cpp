@@ -18,9 +18,12 @@ using namespace bsgp;
 
 struct HostCtx {
     static constexpr bool kFrame = false;
-    int tid = 0, nt = 1, rank = 0, G = 1;
+    int tid = 0, nt = 1, rank = 0, G = 1, parity = 0;
+    void* wst = nullptr;                       // controller state of the one emulated warp
+    template <class S> S* ctl() const { return reinterpret_cast<S*>(wst); }
     void sync() {}
     void cluster_sync() {}
+    void allreduce(int, double*, int) {}
     void allreduce_sum(double*, int) {}
     void allreduce_min(double&) {}
     void allreduce_max(double&) {}
@@ -211,6 +214,8 @@ int emul_solve(int ny, int nx, const bsgp_params* params, const double* gn, cons
     a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
     a.tr_evals = tr_evals;
     HostCtx ctx;
+    CtlState<double> ctl_state;
+    ctx.wst = &ctl_state;
     ImgState<double> S;
     memset(&S, 0, sizeof(S));
     S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem; S.tw_split = 0;
@@ -252,6 +257,8 @@ int emul_solve_wrapped(int iny, int inx, const bsgp_params* params, const double
     a.scalars = scalars; a.tr_alpha = tr_alpha; a.tr_lambda = tr_lambda; a.tr_beta = tr_beta; a.tr_trials = tr_trials;
     a.tr_evals = tr_evals;
     HostCtx ctx;
+    CtlState<double> ctl_state;
+    ctx.wst = &ctl_state;
     ImgState<double> S;
     memset(&S, 0, sizeof(S));
     S.geom = pl.g; S.ws_off = pl.ws_off; S.ppx_off = pl.ppx_off; S.spec = pl.spec.data(); S.twx = pl.twx.data(); S.twy = pl.twy.data(); S.twx_off = kNoSmem; S.twy_off = kNoSmem; S.tw_split = 0;
