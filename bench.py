@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="experiments: do not sample clocks during the timed region")
     ap.add_argument("--cpu-sample", type=int, default=8)
     return ap.parse_args()
 
@@ -324,6 +325,15 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
         return r
 
     # ---------------- value: inputs resident in HBM, sharded solve + gather ----------------
+    if world > 1:
+        # NCCL's first collectives of a given size are several times slower (connection setup, buffer registration): warm the
+        # all-gather up on buffers of the sizes the step uses, so that W warm-up STEPS are enough whatever W the caller picks
+        cap = max(bs.shard.shard_counts(B, world))
+        for shape, dt in (((cap, ny, nx), tdt), ((cap, 2 * (kw.get("MAXIT", 500) + 1) + 6), torch.float64)):
+            src = torch.zeros(shape, dtype=dt, device=dev); dst = torch.empty((world * shape[0],) + shape[1:], dtype=dt, device=dev)
+            for _ in range(8):
+                dist.all_gather_into_tensor(dst, src)
+        del src, dst
     for _ in range(warmup):
         res = step(False)
     barrier()
@@ -532,7 +542,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = dict(bs=bs, dev=dev, rank=rank, local_rank=local_rank, world=world)
-    line = measure(args, ctx, args.workload, args.steps, args.warmup, with_cpu=not args.no_cpu_baseline)
+    line = measure(args, ctx, args.workload, args.steps, args.warmup, with_cpu=not args.no_cpu_baseline, with_clocks=not args.no_clocks)
     if args.workload == "tiles256" and not args.no_extra:
         extra = {}
         if world == 1:
