@@ -1,20 +1,13 @@
 #!/bin/bash
-# A/B of library builds on the same box: csrc/libbsgp_<tag>.so, alternating runs.  usage: gpu_ab.sh <reps> <workloads> tag...
-reps=$1; wl=$2; shift 2
+# A/B of library builds on the three bench workloads.  usage: gpurun -- bash tools/gpu_ab.sh lib1.so lib2.so ...   (paths relative to beta-sgp_b200/csrc)
 mkdir -p gpurun_out
-for rep in $(seq 1 $reps); do
-  for tag in "$@"; do
-    for w in $wl; do
-      BSGP_LIB=$PWD/beta-sgp_b200/csrc/libbsgp_$tag.so python bench.py --steps 3 --warmup 3 --no-cpu-baseline --workload $w > gpurun_out/ab_${w}_${tag}_$rep.json 2>/dev/null
-    done
+for lib in "$@"; do
+  for wl in tiles256 stamps32 frame; do
+    st=3; [ $wl = frame ] && st=2
+    BSGP_LIB=$PWD/beta-sgp_b200/csrc/$lib python bench.py --no-extra --no-cpu-baseline --no-clocks --steps $st --workload $wl 2>/dev/null | grep "^{" | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$lib', '$wl', 'kernel_ms', round(d['roofline']['kernel_ms'],3), 'value', round(d['value'],2), 'frac', round(d['roofline']['frac'],3))
+"
   done
 done
-python - <<PY
-import json, glob, collections
-acc = collections.defaultdict(list)
-for f in sorted(glob.glob("gpurun_out/ab_*.json")):
-    try:
-        d = json.loads(open(f).read().strip().splitlines()[-1]); acc[f.split("/")[-1].rsplit("_", 1)[0]].append(round(d["ms_per_step"], 2))
-    except Exception as e: print(f, "failed", e)
-for k, v in acc.items(): print(k, v, "min", min(v))
-PY
