@@ -303,7 +303,8 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
     host = {k: torch.as_tensor(np.ascontiguousarray(w[k])).to(tdt if k in ("gn", "psf", "bkg") else torch.float64).pin_memory() for k in keys}
     devt = {k: v.to(dev) for k, v in host.items()}
     flux_d = devt.get("flux")
-    beta_np = np.ascontiguousarray(w["beta0"], dtype=np.float64)     # host copy: the dealing (cost ranking) is host logic, no device sync
+    beta_np = np.ascontiguousarray(w["beta0"], dtype=np.float64)
+    cost_rank = bs.shard.expected_cost_rank(B, beta_np, divergence)  # the dealing is host logic: computed once, no device sync in the step
     width = "auto" if args.width == "auto" else tuple(int(v) for v in args.width.split(","))
     if args.cluster or args.threads:
         width = (args.cluster, args.threads)
@@ -318,8 +319,8 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
 
     def step(record):
         t = {} if record else None
-        r = bs.solve_batch_sharded(devt["gn"], devt["psf"], devt["bkg"], flux=flux_d, betaParam=beta_np, divergence=divergence, width=width,
-                                   timing=t, **kw)
+        r = bs.solve_batch_sharded(devt["gn"], devt["psf"], devt["bkg"], flux=flux_d, betaParam=devt["beta0"], divergence=divergence, width=width,
+                                   timing=t, cost_rank=cost_rank, **kw)
         if record:
             timings.append(t)
         return r
@@ -328,7 +329,7 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
     if world > 1:
         # NCCL's first collectives of a given size are several times slower (connection setup, buffer registration): warm the
         # all-gather up on buffers of the sizes the step uses, so that W warm-up STEPS are enough whatever W the caller picks
-        cap = max(bs.shard.shard_counts(B, world))
+        cap = max(bs.shard.shard_counts(B, world, snake=True))
         for shape, dt in (((cap, ny, nx), tdt), ((cap, 2 * (kw.get("MAXIT", 500) + 1) + 6), torch.float64)):
             src = torch.zeros(shape, dtype=dt, device=dev); dst = torch.empty((world * shape[0],) + shape[1:], dtype=dt, device=dev)
             for _ in range(8):
@@ -362,7 +363,6 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
         x_sum = res["x"].sum(dim=(1, 2)).cpu().numpy()
         assert np.abs(x_sum - fl).max() <= 1e-8 * np.abs(fl).max(), "flux not conserved"
     # this rank's share (what its solve kernel processed)
-    cost_rank = bs.shard.expected_cost_rank(B, beta_np, divergence)
     mine = bs.shard.shard_indices(B, rank, world, cost_rank)
     # share of (clusters in flight x kernel time) spent inside solves: 1 - this is queue tail + launch overhead
     t_img = res["times"].cpu().numpy()[mine, iters[mine].astype(int)]
@@ -392,7 +392,7 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
         else:
             r, it = None, torch.zeros(0, dtype=torch.int32, device=dev)
         if world > 1:
-            cap = max(bs.shard.shard_counts(B, world))
+            cap = max(bs.shard.shard_counts(B, world, snake=True))
             pad = torch.zeros(cap, dtype=torch.int32, device=dev); pad[:nl] = it
             allr = torch.empty(world * cap, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(allr, pad)

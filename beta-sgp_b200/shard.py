@@ -31,7 +31,8 @@ def expected_cost_rank(n_items, betaParam=None, divergence="beta"):
 
 def shard_indices(n_items, rank, world_size, cost_rank=None):
     """Indices of the batch entries owned by `rank` (ascending).  Without a ranking: rank, rank + W, rank + 2W, ...;
-    with `cost_rank` (expected_cost_rank): the entries at positions rank, rank + W, ... of that ranking."""
+    with `cost_rank` (expected_cost_rank): the ranking is dealt in snake order (ranks 0..W-1, then W-1..0, ...), so no
+    rank systematically receives the most expensive entry of every round."""
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
     if cost_rank is None:
@@ -39,11 +40,43 @@ def shard_indices(n_items, rank, world_size, cost_rank=None):
     cost_rank = np.asarray(cost_rank)
     if cost_rank.shape != (n_items,):
         raise ValueError("cost_rank must be a permutation of the batch")
-    return np.sort(cost_rank[rank::world_size])
+    pos = np.arange(n_items)
+    rnd, k = pos // world_size, pos % world_size
+    owner = np.where(rnd % 2 == 0, k, world_size - 1 - k)
+    return np.sort(cost_rank[owner == rank])
 
 
-def shard_counts(n_items, world_size):
-    return [len(range(r, n_items, world_size)) for r in range(world_size)]
+def shard_counts(n_items, world_size, snake=False):
+    if not snake:
+        return [len(range(r, n_items, world_size)) for r in range(world_size)]
+    pos = np.arange(n_items)
+    rnd, k = pos // world_size, pos % world_size
+    owner = np.where(rnd % 2 == 0, k, world_size - 1 - k)
+    return [int(np.sum(owner == r)) for r in range(world_size)]
+
+
+_index_cache = {}
+
+
+def _gather_indices(n_items, world_size, cost_rank, dev):
+    """(counts, cap, dest, keep) of the gather, with the two index tensors cached on the device: building them from host
+    arrays every call is a pageable host-to-device copy, which blocks the host until the solve kernel in front of it has
+    finished and so serialises the launches of the gather behind the kernel instead of queueing them under it."""
+    import torch
+    key = (n_items, world_size, str(dev), None if cost_rank is None else np.asarray(cost_rank).tobytes())
+    hit = _index_cache.get(key)
+    if hit is None:
+        parts = [shard_indices(n_items, r, world_size, cost_rank) for r in range(world_size)]
+        counts = [len(p_) for p_ in parts]
+        cap = max(counts) if counts else 0
+        dest = torch.as_tensor(np.concatenate(parts) if n_items else np.zeros(0, np.int64), device=dev, dtype=torch.long)
+        keep = torch.as_tensor(np.concatenate([r * cap + np.arange(counts[r]) for r in range(world_size)]) if n_items else np.zeros(0, np.int64),
+                               device=dev, dtype=torch.long)
+        if len(_index_cache) > 64:
+            _index_cache.clear()
+        hit = _index_cache[key] = (counts, cap, dest, keep)
+    return hit
+
 
 
 def gather_to_all(local, n_items, rank, world_size, group=None, cost_rank=None):
@@ -54,18 +87,13 @@ def gather_to_all(local, n_items, rank, world_size, group=None, cost_rank=None):
     empty shard contribute zero rows."""
     import torch
     import torch.distributed as dist
-    counts = shard_counts(n_items, world_size)
-    cap = max(counts) if counts else 0
     names = list(local)
+    ref = local[names[0]]
+    dev = ref.device
+    counts, cap, dest, keep = _gather_indices(n_items, world_size, cost_rank, dev)
     for name in names:
         if local[name].shape[0] != counts[rank]:
             raise ValueError(f"{name}: expected {counts[rank]} local rows, got {local[name].shape[0]}")
-    ref = local[names[0]]
-    dev = ref.device
-    dest = torch.as_tensor(np.concatenate([shard_indices(n_items, r, world_size, cost_rank) for r in range(world_size)]) if n_items else
-                           np.zeros(0, np.int64), device=dev, dtype=torch.long)
-    keep = torch.as_tensor(np.concatenate([r * cap + np.arange(counts[r]) for r in range(world_size)]) if n_items else np.zeros(0, np.int64),
-                           device=dev, dtype=torch.long)
 
     def gather(t):
         """[n_local, k] -> [n_items, k] in batch order"""
@@ -99,7 +127,7 @@ _FIELDS = ("x", "iters", "status", "discr", "times", "beta_final", "proj_evals",
 
 
 def solve_batch_sharded(gn, psf, bkg, flux=None, betaParam=1.005, x0=None, obj=None, divergence="beta", group=None, device=None,
-                        width="auto", timing=None, **kw):
+                        width="auto", timing=None, cost_rank=None, **kw):
     """Every rank passes the FULL batch and gets the full result back: rank r restores the images
     shard_indices(B, r, W, expected_cost_rank(...)) on its own GPU (engine.solve_batch, one persistent kernel launch) and
     the per-image results are all-gathered.  No data-path collective: the images are independent problems.
@@ -108,6 +136,8 @@ def solve_batch_sharded(gn, psf, bkg, flux=None, betaParam=1.005, x0=None, obj=N
     the device, asynchronously on the current stream; NCCL process group required when world_size > 1).
     psf: [ny,nx] shared or [B,ny,nx]; bkg: scalar, [B] or [B,ny,nx]; flux / betaParam: scalar or [B]; x0 / obj: [B,ny,nx].
     width: "auto" picks the CTA configuration from the local batch size (engine.auto_config), or (cluster_size, threads).
+    cost_rank: optional precomputed expected_cost_rank(...) (a host array); give it when betaParam is a device tensor, so
+    that the dealing does not have to copy betaParam back to the host (a synchronisation) on every call.
     timing: optional dict; with CUDA tensors it receives timing["solve"] = (start, end) CUDA events around the local solve
     (what bench.py divides the algorithmic bytes by) and timing["plan"] = the plan's info."""
     import torch
@@ -121,8 +151,10 @@ def solve_batch_sharded(gn, psf, bkg, flux=None, betaParam=1.005, x0=None, obj=N
         device = (gn.device.index or 0) if on_dev else int(__import__("os").environ.get("LOCAL_RANK", rank))
     B = int(gn.shape[0])
     ny, nx = int(gn.shape[-2]), int(gn.shape[-1])
-    b_host = betaParam.detach().cpu().numpy() if engine._is_tensor(betaParam) else betaParam
-    cost_rank = expected_cost_rank(B, b_host, divergence)
+    if cost_rank is None:
+        b_host = betaParam.detach().cpu().numpy() if engine._is_tensor(betaParam) else betaParam
+        cost_rank = expected_cost_rank(B, b_host, divergence)
+    cost_rank = np.ascontiguousarray(cost_rank)
     idx = shard_indices(B, rank, world, cost_rank)
     n_local = len(idx)
     use_cuda = on_dev or (is_dist and dist.get_backend(group) == "nccl")
@@ -130,7 +162,10 @@ def solve_batch_sharded(gn, psf, bkg, flux=None, betaParam=1.005, x0=None, obj=N
     maxit = int(kw.get("MAXIT", 500))
 
     if on_dev:
-        sel = torch.as_tensor(idx, device=gn.device, dtype=torch.long)
+        skey = ("sel", B, rank, world, str(gn.device), cost_rank.tobytes())
+        sel = _index_cache.get(skey)
+        if sel is None:
+            sel = _index_cache[skey] = torch.as_tensor(idx, device=gn.device, dtype=torch.long)
 
         def take(a, per_image_ndim):
             if a is None:

@@ -29,7 +29,7 @@ def test_shard_indices_partition():
                 cr = sh.expected_cost_rank(n, beta) if ranked else None
                 parts = [sh.shard_indices(n, r, w, cr) for r in range(w)]
                 assert sorted(np.concatenate(parts).tolist()) == list(range(n))
-                assert [len(p) for p in parts] == sh.shard_counts(n, w)
+                assert [len(p) for p in parts] == sh.shard_counts(n, w, snake=ranked)
                 assert max(map(len, parts)) - min(map(len, parts)) <= 1
 
 
@@ -53,7 +53,7 @@ def _worker(rank, world, n, port, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sh = _shard_module()
-    idx = sh.shard_indices(n, rank, world)
+    idx = sh.shard_indices(n, rank, world)                 # plain round-robin (no cost ranking)
     # stand-in for the per-image solve: a deterministic function of the global image index
     x = torch.stack([torch.full((4, 4), float(i)) for i in idx]) if len(idx) else torch.zeros(0, 4, 4)
     iters = torch.tensor([3 * int(i) + 1 for i in idx], dtype=torch.int32)
@@ -111,7 +111,7 @@ def _front_end_worker(rank, world, n, port, ret):
         want = _fake_result(bs, args["gn"], args["psf"], args["bkg"], args["flux"], args["betaParam"], args["x0"], args["obj"], 5)
         for k in ("x", "iters", "status", "discr", "times", "beta_final", "proj_evals", "ls_trials"):
             ok = ok and np.array_equal(full[k], getattr(want, k)) and full[k].dtype == getattr(want, k).dtype
-        ok = ok and seen.get("n", 0) == len(range(rank, n, world))
+        ok = ok and seen.get("n", 0) == bs.shard.shard_counts(n, world, snake=True)[rank]
         seen.clear()
     ret[rank] = ok
     dist.barrier()
