@@ -97,22 +97,25 @@ template <typename T> BSGP_DEV DivK<T> make_divk(int divergence, double beta) {
 //   beta  : acc0 += k*gn^b (only if want_s1), acc1 += k(b-1)*den^b, acc2 += k*b*gn*den^(b-1)   sgp.py:457-458
 //   b == 0: acc0 += gn/den, acc1 += log(gn/den)                                     sgp.py:453
 //   b == 1: acc0 += gn*log(gn/den), acc1 += gn, acc2 += den                         sgp.py:455
-template <typename T> BSGP_DEV T objective_pixel(const DivK<T>& dk, T gnv, T den, T xtf_try, bool want_s1, KSum* acc) {
-    if (dk.kind == 0) {
+// KIND / S1 are compile-time in the solver's phases: each phase exists once per divergence kind (and, for the generic
+// beta-divergence, with / without the sum of k*gn^beta), so a solve only ever touches the code of its own kind - the phases
+// that evaluate the objective are the largest functions of the kernel (two inlined pow() per pixel pair and row).
+template <int KIND, bool S1, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, T gnv, T den, T xtf_try, KSum* acc) {
+    if (KIND == 0) {
         const T ratio = ndiv(gnv, den);
         acc[0].add((double)nmul(gnv, mlog(ratio)));
         acc[1].add((double)xtf_try);
         return ratio;
     }
-    if (dk.kind == 1) {
+    if (KIND == 1) {
         const T p1 = mpow(den, dk.bm1);
         acc[1].add((double)nmul(dk.k2, nmul(p1, den)));
         acc[2].add((double)nmul(nmul(dk.k3, gnv), p1));
-        if (want_s1) acc[0].add((double)nmul(dk.k, mpow(gnv, dk.b)));
+        if (S1) acc[0].add((double)nmul(dk.k, mpow(gnv, dk.b)));
         return p1;
     }
     const T ratio = ndiv(gnv, den);
-    if (dk.kind == 2) {
+    if (KIND == 2) {
         acc[0].add((double)ratio);
         acc[1].add((double)mlog(ratio));
         return ndiv((T)1, den);
@@ -122,6 +125,19 @@ template <typename T> BSGP_DEV T objective_pixel(const DivK<T>& dk, T gnv, T den
     acc[2].add((double)den);
     return (T)1;
 }
+template <typename T> BSGP_DEV T objective_pixel(const DivK<T>& dk, T gnv, T den, T xtf_try, bool want_s1, KSum* acc) {
+    if (dk.kind == 0) return objective_pixel_k<0, false>(dk, gnv, den, xtf_try, acc);
+    if (dk.kind == 1) return want_s1 ? objective_pixel_k<1, true>(dk, gnv, den, xtf_try, acc) : objective_pixel_k<1, false>(dk, gnv, den, xtf_try, acc);
+    if (dk.kind == 2) return objective_pixel_k<2, false>(dk, gnv, den, xtf_try, acc);
+    return objective_pixel_k<3, false>(dk, gnv, den, xtf_try, acc);
+}
+
+// call phase FN<T, MK, KIND, S1>(...) with the divergence kind (and want_s1 for the generic beta-divergence) as compile-time constants
+#define BSGP_DISPATCH_KIND(dk, want_s1, FN, ...)                                                             \
+    ((dk).kind == 0 ? FN<T, MK, 0, false>(__VA_ARGS__)                                                       \
+     : (dk).kind == 1 ? ((want_s1) ? FN<T, MK, 1, true>(__VA_ARGS__) : FN<T, MK, 1, false>(__VA_ARGS__))     \
+     : (dk).kind == 2 ? FN<T, MK, 2, false>(__VA_ARGS__)                                                     \
+                      : FN<T, MK, 3, false>(__VA_ARGS__))
 
 template <typename T> BSGP_DEV double objective_value(const DivK<T>& dk, const double* acc, double s1, double flux, double npix) {
     if (dk.kind == 0) return (acc[0] + acc[1]) - flux;
@@ -327,7 +343,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
-template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
     const Region R = region_of<MK>(ctx, S);
@@ -337,7 +353,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0(Ctx ctx, c
     auto one = [&](bool m, T gnv, T bk, T v, T& xt, T& p) {
         if (!m) { xt = (T)0; p = (T)0; return; }
         xt = MK ? ndiv(v, div) : v;
-        p = objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+        p = objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
         V2<T> xt, p;
@@ -488,7 +504,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx
 }
 
 // consumer of A(d): d_tf, first line-search trial (lam = 1) fused            sgp.py:326-334
-template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, const ImgState<T>* S, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_ri_trial_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
     const Region R = region_of<MK>(ctx, S);
@@ -499,7 +515,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_ri_trial(Ctx ctx, 
         if (!m) { dt = (T)0; p = (T)0; return; }
         dt = MK ? ndiv(v, div) : v;
         const T xt = nadd(xtfv, dt);                       // lam = 1
-        p = objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+        p = objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
         V2<T> dt, p;
@@ -532,7 +548,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx,
 }
 
 // one more line-search trial: objective at x_tf + lam d_tf                  sgp.py:329-334
-template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk, int want_s1) {
+template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_trial_k(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk) {
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
@@ -545,7 +561,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_trial(Ctx ctx, con
     auto one = [&](bool m, T xtfv, T dtfv, T bk, T gnv) -> T {
         if (!m) return (T)0;
         const T xt = nadd(xtfv, nmul(lam, dtfv));
-        return objective_pixel(dk, gnv, nadd(xt, bk), xt, want_s1 != 0, acc);
+        return objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto body = [&](int i, const In4<T>& in) {
         V2<T> p;
@@ -840,7 +856,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         conv_middle<T>(ctx, S, S->tf, CONV_TF);
         double acc[3];
         {
-            const R3 o = ph_ri_obj0<T, MK>(ctx, S, W->dk, !W->s1_valid);
+            const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_ri_obj0_k, ctx, S, W->dk);
             acc[0] = o.a; acc[1] = o.b; acc[2] = o.c;
         }
         allreduce_fn<0, 3>(ctx, acc);
@@ -926,7 +942,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             W->pending = 0;
             conv_middle<T>(ctx, S, S->tf, CONV_TF);
             {
-                const R3 o = ph_ri_trial<T, MK>(ctx, S, W->dk, !W->s1_valid);
+                const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_ri_trial_k, ctx, S, W->dk);
                 sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             }
             allreduce_fn<0, 4>(ctx, sums);
@@ -952,7 +968,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             W->lam = nmul(W->lam, P.ls_beta);
             W->trials += 1;
             double sums[3];
-            const R3 o = ph_trial<T, MK>(ctx, S, (T)W->lam, W->dk, !W->s1_valid);
+            const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_trial_k, ctx, S, (T)W->lam, W->dk);
             sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             allreduce_fn<0, 3>(ctx, sums);
             if (W->dk.kind == 1 && !W->s1_valid) { W->s1 = sums[0]; W->s1_valid = 1; }
