@@ -111,9 +111,10 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
     for (int tile = 0; tile < ntiles; ++tile) {
         const int pair0 = tile * g.row_tile_pairs;
         const int total = g.row_tile_pairs << g.lg_hx;      // steps: one row pair x one column pair
-        // full batches without guards (a guarded assignment would push the register tile into local memory)
+        // full batches without guards (a guarded assignment would push the register tile into local memory); with U == 1 a
+        // batch is exactly one step of the loop below, so the batched copy of the (large, inlined) producer is left out
         int e0 = ctx.tid;
-        for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+        for (; U > 1 && e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
             decltype(fetch(0)) in0[U], in1[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -338,7 +339,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
         else fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
         {
             int e0 = ctx.tid;
-            for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+            for (; U > 1 && e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
                 decltype(fetch(0)) in0[U], in1[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -380,7 +381,7 @@ template <int U, class Ctx, class Fetch, class Body>
 BSGP_DEV void pair_loop(Ctx& ctx, int n, Fetch& fetch, Body& body) {
     const int np = n >> 1;
     int q0 = ctx.tid;
-    for (; q0 + (U - 1) * ctx.nt < np; q0 += ctx.nt * U) {          // full batches: no guards, the tile stays in registers
+    for (; U > 1 && q0 + (U - 1) * ctx.nt < np; q0 += ctx.nt * U) {  // full batches: no guards, the tile stays in registers (U == 1: the loop below is the same)
         decltype(fetch(0)) in[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) in[u] = fetch(2 * (q0 + u * ctx.nt));

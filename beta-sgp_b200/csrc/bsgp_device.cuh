@@ -80,6 +80,7 @@ struct DeviceCtx {
         if (tid < G * k) {
             const int dst = tid / k, j = tid - dst * k;
             double s = sh->warp_part[0][j];
+#pragma unroll 1          // compact code: the all-reduces are real functions now and part of every iteration's instruction footprint
             for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][j]);
             if (G == 1) {
                 sh->inbox[half][0][j] = s;
@@ -107,10 +108,10 @@ struct DeviceCtx {
             }
             parity ^= 2 << half;
         }
-        for (int j = 0; j < k; ++j) {
-            double s = sh->inbox[half][0][j];
-            for (int r = 1; r < G; ++r) s = red_combine(op, s, sh->inbox[half][r][j]);
-            v[j] = s;
+        for (int j = 0; j < k; ++j) v[j] = sh->inbox[half][0][j];
+#pragma unroll 1
+        for (int r = 1; r < G; ++r) {
+            for (int j = 0; j < k; ++j) v[j] = red_combine(op, v[j], sh->inbox[half][r][j]);
         }
         parity ^= 1;
     }
