@@ -21,7 +21,7 @@ constexpr int kMaxG = 16;
 constexpr int kMaxK = 8;
 
 struct SharedCtl {
-    double warp_part[kMaxWarps][kMaxK];
+    double warp_part[2][kMaxWarps][kMaxK];   // two halves (parity bit 0), so that a single-CTA all-reduce needs one barrier only
     double inbox[2][kMaxG][kMaxK];
     unsigned long long mbar[2];     // transaction barriers of the two inbox halves (cluster all-reduce)
     int next_img;
@@ -73,27 +73,32 @@ struct DeviceCtx {
             double x = v[j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
-            if (lane == 0) sh->warp_part[warp][j] = x;
+            if (lane == 0) sh->warp_part[half][warp][j] = x;
         }
         __syncthreads();
+        if (G == 1) {
+            // one CTA per image (stamps): every thread adds the warp partials itself, in warp order; the other half of
+            // warp_part is free for the next all-reduce (a thread is at most one all-reduce ahead of the slowest one)
+            for (int j = 0; j < k; ++j) v[j] = sh->warp_part[half][0][j];
+#pragma unroll 1
+            for (int w = 1; w < nwarps; ++w) {
+                for (int j = 0; j < k; ++j) v[j] = red_combine(op, v[j], sh->warp_part[half][w][j]);
+            }
+            parity ^= 1;
+            return;
+        }
         const unsigned bar = smem_u32(&sh->mbar[half]);
         if (tid < G * k) {
             const int dst = tid / k, j = tid - dst * k;
-            double s = sh->warp_part[0][j];
+            double s = sh->warp_part[half][0][j];
 #pragma unroll 1          // compact code: the all-reduces are real functions now and part of every iteration's instruction footprint
-            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][j]);
-            if (G == 1) {
-                sh->inbox[half][0][j] = s;
-            } else {
-                const unsigned slot = map_to_rank(smem_u32(&sh->inbox[half][rank][j]), dst);
-                const unsigned rbar = map_to_rank(bar, dst);
-                asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
-                             :: "r"(slot), "l"(__double_as_longlong(s)), "r"(rbar) : "memory");
-            }
+            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[half][w][j]);
+            const unsigned slot = map_to_rank(smem_u32(&sh->inbox[half][rank][j]), dst);
+            const unsigned rbar = map_to_rank(bar, dst);
+            asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                         :: "r"(slot), "l"(__double_as_longlong(s)), "r"(rbar) : "memory");
         }
-        if (G == 1) {
-            __syncthreads();
-        } else {
+        {
             if (tid == 0) {
                 unsigned long long state;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;"
@@ -171,12 +176,12 @@ struct GridCtx {
             double x = v[j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, o));
-            if (lane == 0) sh->warp_part[warp][j] = x;
+            if (lane == 0) sh->warp_part[0][warp][j] = x;
         }
         __syncthreads();
         if (tid < k) {
-            double s = sh->warp_part[0][tid];
-            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[w][tid]);
+            double s = sh->warp_part[0][0][tid];
+            for (int w = 1; w < nwarps; ++w) s = red_combine(op, s, sh->warp_part[0][w][tid]);
             gpart[((size_t)half * G + rank) * kMaxK + tid] = s;
         }
         cg::this_grid().sync();

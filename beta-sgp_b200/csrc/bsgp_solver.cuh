@@ -29,6 +29,16 @@
 #include "bsgp_conv.cuh"
 #include "bsgp_project.cuh"
 
+#ifndef BSGP_U_TRIAL
+#define BSGP_U_TRIAL 2
+#endif
+#ifndef BSGP_U_TP
+#define BSGP_U_TP 4
+#endif
+#ifndef BSGP_U_PE
+#define BSGP_U_PE 8
+#endif
+
 namespace bsgp {
 
 enum Buf { B_GN = 0, B_BKG, B_X, B_G, B_XTF, B_D, B_DTF, B_T1, NBUF };
@@ -293,7 +303,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_proj_eval(Ctx 
         if (inside<MK>(R, i)) s += (double)proj_point(in.a.x, in.b.x, lam, has_cap, cap);
         if (inside<MK>(R, i + 1)) s += (double)proj_point(in.a.y, in.b.y, lam, has_cap, cap);
     };
-    pair_loop<8>(ctx, S->nslab, fetch, body);
+    pair_loop<BSGP_U_PE>(ctx, S->nslab, fetch, body);
     return s;
 }
 
@@ -455,7 +465,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R3 ph_trial_point(Ctx ct
         st2(cbuf, i, co);
         st2(Xbuf, i, Xo);
     };
-    pair_loop<4>(ctx, S->nslab, fetch, body);
+    pair_loop<BSGP_U_TP>(ctx, S->nslab, fetch, body);
     R3 r; r.a = s0; r.b = sp; r.c = sm;
     return r;
 }
@@ -569,7 +579,7 @@ template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph
         p.y = one(inside<MK>(R, i + 1), in.a.y, in.b.y, in.c.y, in.d.y);
         st2(t1, i, p);
     };
-    pair_loop<2>(ctx, S->nslab, fetch, body);
+    pair_loop<BSGP_U_TRIAL>(ctx, S->nslab, fetch, body);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
 }
