@@ -107,10 +107,11 @@ template <typename T> BSGP_DEV DivK<T> make_divk(int divergence, double beta) {
 //   beta  : acc0 += k*gn^b (only if want_s1), acc1 += k(b-1)*den^b, acc2 += k*b*gn*den^(b-1)   sgp.py:457-458
 //   b == 0: acc0 += gn/den, acc1 += log(gn/den)                                     sgp.py:453
 //   b == 1: acc0 += gn*log(gn/den), acc1 += gn, acc2 += den                         sgp.py:455
-// KIND / S1 are compile-time in the solver's phases: each phase exists once per divergence kind (and, for the generic
-// beta-divergence, with / without the sum of k*gn^beta), so a solve only ever touches the code of its own kind - the phases
-// that evaluate the objective are the largest functions of the kernel (two inlined pow() per pixel pair and row).
-template <int KIND, bool S1, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, T gnv, T den, T xtf_try, KSum* acc) {
+// KIND is compile-time in the solver's phases: each phase exists once per divergence kind, so a solve only ever touches
+// the code of its own kind - the phases that evaluate the objective are the largest functions of the kernel (an inlined
+// pow() per pixel of every pair and row).  The data-only term of the generic beta-divergence, s1 = sum k*gn^beta, changes
+// only when beta does: it has its own small pass (ph_s1) instead of a second pow() in every objective phase.
+template <int KIND, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, T gnv, T den, T xtf_try, KSum* acc) {
     if (KIND == 0) {
         const T ratio = ndiv(gnv, den);
         acc[0].add((double)nmul(gnv, mlog(ratio)));
@@ -121,7 +122,6 @@ template <int KIND, bool S1, typename T> BSGP_DEV T objective_pixel_k(const DivK
         const T p1 = mpow(den, dk.bm1);
         acc[1].add((double)nmul(dk.k2, nmul(p1, den)));
         acc[2].add((double)nmul(nmul(dk.k3, gnv), p1));
-        if (S1) acc[0].add((double)nmul(dk.k, mpow(gnv, dk.b)));
         return p1;
     }
     const T ratio = ndiv(gnv, den);
@@ -136,18 +136,21 @@ template <int KIND, bool S1, typename T> BSGP_DEV T objective_pixel_k(const DivK
     return (T)1;
 }
 template <typename T> BSGP_DEV T objective_pixel(const DivK<T>& dk, T gnv, T den, T xtf_try, bool want_s1, KSum* acc) {
-    if (dk.kind == 0) return objective_pixel_k<0, false>(dk, gnv, den, xtf_try, acc);
-    if (dk.kind == 1) return want_s1 ? objective_pixel_k<1, true>(dk, gnv, den, xtf_try, acc) : objective_pixel_k<1, false>(dk, gnv, den, xtf_try, acc);
-    if (dk.kind == 2) return objective_pixel_k<2, false>(dk, gnv, den, xtf_try, acc);
-    return objective_pixel_k<3, false>(dk, gnv, den, xtf_try, acc);
+    if (dk.kind == 0) return objective_pixel_k<0>(dk, gnv, den, xtf_try, acc);
+    if (dk.kind == 1) {
+        if (want_s1) acc[0].add((double)nmul(dk.k, mpow(gnv, dk.b)));
+        return objective_pixel_k<1>(dk, gnv, den, xtf_try, acc);
+    }
+    if (dk.kind == 2) return objective_pixel_k<2>(dk, gnv, den, xtf_try, acc);
+    return objective_pixel_k<3>(dk, gnv, den, xtf_try, acc);
 }
 
-// call phase FN<T, MK, KIND, S1>(...) with the divergence kind (and want_s1 for the generic beta-divergence) as compile-time constants
-#define BSGP_DISPATCH_KIND(dk, want_s1, FN, ...)                                                             \
-    ((dk).kind == 0 ? FN<T, MK, 0, false>(__VA_ARGS__)                                                       \
-     : (dk).kind == 1 ? ((want_s1) ? FN<T, MK, 1, true>(__VA_ARGS__) : FN<T, MK, 1, false>(__VA_ARGS__))     \
-     : (dk).kind == 2 ? FN<T, MK, 2, false>(__VA_ARGS__)                                                     \
-                      : FN<T, MK, 3, false>(__VA_ARGS__))
+// call phase FN<T, MK, KIND>(...) with the divergence kind as a compile-time constant
+#define BSGP_DISPATCH_KIND(dk, FN, ...)                         \
+    ((dk).kind == 0 ? FN<T, MK, 0>(__VA_ARGS__)                  \
+     : (dk).kind == 1 ? FN<T, MK, 1>(__VA_ARGS__)                \
+     : (dk).kind == 2 ? FN<T, MK, 2>(__VA_ARGS__)                \
+                      : FN<T, MK, 3>(__VA_ARGS__))
 
 template <typename T> BSGP_DEV double objective_value(const DivK<T>& dk, const double* acc, double s1, double flux, double npix) {
     if (dk.kind == 0) return (acc[0] + acc[1]) - flux;
@@ -353,7 +356,7 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const Im
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
-template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
+template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
     const T* gn = S->gn; const T* bkgb = S->bkg; T* xtf = S->xtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
     const Region R = region_of<MK>(ctx, S);
@@ -363,7 +366,7 @@ template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph
     auto one = [&](bool m, T gnv, T bk, T v, T& xt, T& p) {
         if (!m) { xt = (T)0; p = (T)0; return; }
         xt = MK ? ndiv(v, div) : v;
-        p = objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
+        p = objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
         V2<T> xt, p;
@@ -514,7 +517,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx
 }
 
 // consumer of A(d): d_tf, first line-search trial (lam = 1) fused            sgp.py:326-334
-template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_ri_trial_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
+template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_ri_trial_k(Ctx ctx, const ImgState<T>* S, DivK<T> dk) {
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s; const T div = S->div_a;
     const Region R = region_of<MK>(ctx, S);
@@ -525,7 +528,7 @@ template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph
         if (!m) { dt = (T)0; p = (T)0; return; }
         dt = MK ? ndiv(v, div) : v;
         const T xt = nadd(xtfv, dt);                       // lam = 1
-        p = objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
+        p = objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
         V2<T> dt, p;
@@ -537,6 +540,22 @@ template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph
     conv_rows_inverse<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, cf, ca);
     R3 r; r.a = acc[0].value(); r.b = acc[1].value(); r.c = acc[2].value();
     return r;
+}
+
+// slab part of s1 = sum k * gn^beta, the data-only term of the generic beta-divergence       sgp.py:457
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_s1(Ctx ctx, const ImgState<T>* S, T k, T b) {
+    ctx.sync();
+    const T* gn = S->gn;
+    const Region R = region_of<MK>(ctx, S);
+    KSum acc;
+    acc.clear();
+    auto fetch = [&](int i) { In1<T> r; r.a = ld2(gn, i); return r; };
+    auto body = [&](int i, const In1<T>& in) {
+        if (inside<MK>(R, i)) acc.add((double)nmul(k, mpow(in.a.x, b)));
+        if (inside<MK>(R, i + 1)) acc.add((double)nmul(k, mpow(in.a.y, b)));
+    };
+    pair_loop<1>(ctx, S->nslab, fetch, body);
+    return acc.value();
 }
 
 // slab part of sum dD_beta/dbeta at the rejected trial point               sgp.py:798-800
@@ -558,7 +577,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx,
 }
 
 // one more line-search trial: objective at x_tf + lam d_tf                  sgp.py:329-334
-template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph_trial_k(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk) {
+template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_trial_k(Ctx ctx, const ImgState<T>* S, T lam, DivK<T> dk) {
     ctx.sync();
     const T* gn = S->gn; const T* bkgb = S->bkg; const T* xtf = S->xtf; const T* dtf = S->dtf; T* t1 = S->t1;
     const bool bimg = S->bkg_img != 0; const T bkg_s = S->bkg_s;
@@ -571,7 +590,7 @@ template <typename T, bool MK, int KIND, bool S1, class Ctx> BSGP_NOINLINE R3 ph
     auto one = [&](bool m, T xtfv, T dtfv, T bk, T gnv) -> T {
         if (!m) return (T)0;
         const T xt = nadd(xtfv, nmul(lam, dtfv));
-        return objective_pixel_k<KIND, S1>(dk, gnv, nadd(xt, bk), xt, acc);
+        return objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto body = [&](int i, const In4<T>& in) {
         V2<T> p;
@@ -858,6 +877,13 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
     W->dk = make_divk<T>(P.divergence, W->beta_p);
     W->s1 = 0.0;              // sum k*gn^beta for the current beta
     W->s1_valid = 0;
+    auto refresh_s1 = [&]() {                                            // after beta changed (and once at the start)
+        if (W->dk.kind == 1 && !W->s1_valid) {
+            double s = ph_s1<T, MK>(ctx, S, W->dk.k, W->dk.b);
+            allreduce_fn<0, 1>(ctx, &s);
+            W->s1 = s; W->s1_valid = 1;
+        }
+    };
     W->fv = 0.0; W->x_low = 0.0; W->x_upp = 0.0;
 
     if (W->status == BSGP_ST_OK) {
@@ -866,11 +892,11 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         conv_middle<T>(ctx, S, S->tf, CONV_TF);
         double acc[3];
         {
-            const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_ri_obj0_k, ctx, S, W->dk);
+            const R3 o = BSGP_DISPATCH_KIND(W->dk, ph_ri_obj0_k, ctx, S, W->dk);
             acc[0] = o.a; acc[1] = o.b; acc[2] = o.c;
         }
         allreduce_fn<0, 3>(ctx, acc);
-        if (W->dk.kind == 1) { W->s1 = acc[0]; W->s1_valid = 1; }
+        refresh_s1();
         W->fv = objective_value(W->dk, acc, W->s1, W->flux, W->npix_d);
         // ---------------------------------------------------------------- gradient
         ph_rf_grad<T, MK>(ctx, S, W->dk.kind, (T)0, F_FIRST);
@@ -952,12 +978,12 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             W->pending = 0;
             conv_middle<T>(ctx, S, S->tf, CONV_TF);
             {
-                const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_ri_trial_k, ctx, S, W->dk);
+                const R3 o = BSGP_DISPATCH_KIND(W->dk, ph_ri_trial_k, ctx, S, W->dk);
                 sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             }
             allreduce_fn<0, 4>(ctx, sums);
             W->gd = sums[3];
-            if (W->dk.kind == 1 && !W->s1_valid) { W->s1 = sums[0]; W->s1_valid = 1; }
+            refresh_s1();
             W->fv = objective_value(W->dk, sums, W->s1, W->flux, W->npix_d);
             const int M = P.m;
             double f_ref = W->f_hist[0];                                     // fr = max(Fold)
@@ -978,10 +1004,10 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             W->lam = nmul(W->lam, P.ls_beta);
             W->trials += 1;
             double sums[3];
-            const R3 o = BSGP_DISPATCH_KIND(W->dk, !W->s1_valid, ph_trial_k, ctx, S, (T)W->lam, W->dk);
+            const R3 o = BSGP_DISPATCH_KIND(W->dk, ph_trial_k, ctx, S, (T)W->lam, W->dk);
             sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
             allreduce_fn<0, 3>(ctx, sums);
-            if (W->dk.kind == 1 && !W->s1_valid) { W->s1 = sums[0]; W->s1_valid = 1; }
+            refresh_s1();
             W->fv = objective_value(W->dk, sums, W->s1, W->flux, W->npix_d);
         }
         W->total_trials += W->trials;
