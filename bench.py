@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tiles256", choices=["tiles256", "stamps32", "frame", "ngc", "sat"])
+    ap.add_argument("--workload", default="tiles256", choices=["tiles256", "stamps32", "cutouts31", "frame", "ngc", "sat"])
     ap.add_argument("--no-extra", action="store_true", help="skip the brief runs of the other BASELINE configs (key 'workloads')")
     ap.add_argument("--width", default="auto", help="CTA configuration of the sharded solve: auto or cluster,threads")
     ap.add_argument("--field", type=int, default=2048, help="side of the synthetic field (tiles256)")
@@ -97,6 +97,15 @@ def make_workload(args, rank):
             kw = dict(init_recon=3, proj_type=1, stop_criterion=1, MAXIT=332, adapt_beta=False)
             name = ("config2: beta-SGP with the flux-conserving projection on satellite_25500.mat (256x256), beta=1.0001, 332 iterations "
                     "(simulation_test_sgp.py:154), single image")
+        return w, kw, name, True
+    if args.workload == "cutouts31":
+        # the literal shape of application_sgp_star_stamps.py:24,58,82-89: 31 x 31 cut-outs restored with the 31 x 31 PSF image the
+        # reference ships (psf/psfccfbrd210048_1_1_img.fits; its pixels are committed in tests/golden/psf_golden.npz), one PSF for all
+        psf31 = np.load(os.path.join(ROOT, "tests", "golden", "psf_golden.npz"))["shipped"].astype(np.float64)
+        w = synth.star_cutouts(args.stamps, psf31, seed=31)
+        kw = dict(synth.STAMP_KWARGS)
+        name = (f"config3b: {args.stamps} synthetic 31x31 star cut-outs with the 31x31 PSF image shipped by the reference (shared), the call of "
+                "application_sgp_star_stamps.py:82-89; odd side -> wrapped plan (64x64 FFT grid, fold)")
         return w, kw, name, True
     w = synth.star_stamps(args.stamps, 32, seed=12345)
     kw = dict(synth.STAMP_KWARGS)
@@ -439,7 +448,7 @@ def measure(args, ctx, workload, steps, warmup, with_cpu, sharded=True, with_clo
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get(workload), tj.get("source")
     total_iters = float(iters.sum())
-    on_chip = ny * nx * wbytes <= 64 * 1024
+    on_chip = (info["resident_mask"] & 0xFF) == 0xFF          # every per-image array of the solver lives in shared memory
     line = {
         "metric": "beta-SGP restored images/s", "value": value, "unit": "images/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -548,7 +557,7 @@ def main():
         if world == 1:
             # the other BASELINE configs, briefly (each: W >= 3 warm-up steps; inputs of 3 and 5 exceed L2, 1 and 2 are single-image latency)
             for name, wl, st in (("config1_kl_ngc7027", "ngc", 5), ("config2_beta_proj_satellite", "sat", 3), ("config3_stamps_8192", "stamps32", 5),
-                                 ("config5_frame_8192", "frame", 2)):
+                                 ("config3b_cutouts31_8192", "cutouts31", 3), ("config5_frame_8192", "frame", 2)):
                 try:
                     extra[name] = brief(measure(args, ctx, wl, st, 3, with_cpu=not args.no_cpu_baseline, with_clocks=False))
                 except Exception as e:                    # a failing side workload must not take the headline line with it
