@@ -56,11 +56,19 @@ enum ConvMode { CONV_TF = 0, CONV_CTF = 1, CONV_MAKE_TF = 2 };
 
 // the scalars of ConvGeom the row passes need, copied to registers once per pass (the geometry itself
 // lives in shared memory, where every store through another pointer would force a reload)
-struct RowGeom { int nx, hx, lg_nx, lg_hx, lg_ny, lg_cp, rows_per_cta, row_tile_pairs, rowstride, ps, wrap_nx; };
-BSGP_DEV RowGeom row_geom(const ConvGeom& g) {
+// Row transform of length n = fft_len(px) (nx itself, or a shorter dense DFT): frequency k pairs with its mirror n - k for
+// k = 1 .. kmax = (n - 1) / 2; an even n has a Nyquist frequency nyq = n / 2 whose (real) coefficient shares packed
+// column 0 with the DC term (nyq = -1: odd n, no such term).  Packed columns beyond kmax carry zeros.
+// GEN (compile time) enables all of this plus the folds of wrapped plans; it is set in the kernels of embedded plans
+// only (MK = true: images that are not a power-of-two grid by themselves), so that the power-of-two path, which is
+// bound by instruction fetch on small images and by registers on large ones, carries none of it.
+struct RowGeom { int nx, hx, lg_nx, lg_hx, lg_ny, lg_cp, rows_per_cta, row_tile_pairs, rowstride, ps, wrap_nx, nmir, kmax, nyq; };
+template <bool GEN> BSGP_DEV RowGeom row_geom(const ConvGeom& g) {
     RowGeom r;
     r.nx = g.nx; r.hx = g.hx; r.lg_nx = g.lg_nx; r.lg_hx = g.lg_hx; r.lg_ny = g.lg_ny; r.lg_cp = g.lg_cp; r.rows_per_cta = g.rows_per_cta;
     r.row_tile_pairs = g.row_tile_pairs; r.rowstride = g.rowstride; r.ps = g.px.pad_shift; r.wrap_nx = g.wrap_nx;
+    if (GEN) { r.nmir = fft_len(g.px); r.kmax = (r.nmir - 1) >> 1; r.nyq = (r.nmir & 1) ? -1 : (r.nmir >> 1); }
+    else { r.nmir = g.nx; r.kmax = g.hx - 1; r.nyq = g.hx; }      // never read: the !GEN code uses nx and hx directly
     return r;
 }
 
@@ -99,11 +107,11 @@ template <class Ctx> BSGP_DEV void fill_pos_table(Ctx& ctx, const FftPlan& pl, u
 }
 
 // Producer: In fetch(i); V2 eval(i, In) for the slab pixel pair (i, i + 1), i = local_row * nx + col.
-template <int U, class Ctx, typename T, class Fetch, class Eval>
+template <int U, bool GEN = false, class Ctx, typename T, class Fetch, class Eval>
 BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, cplx<T>* spec, Fetch& fetch, Eval& eval) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
-    const RowGeom g = row_geom(gg);                          // scalars in registers; the FFT plan stays where it is
+    const RowGeom g = row_geom<GEN>(gg);                     // scalars in registers; the FFT plan stays where it is
     const FftPlan& px = gg.px;
     const int r0 = ctx.rank * g.rows_per_cta;
     const int ps = g.ps;
@@ -148,19 +156,21 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
         }
         ctx.sync();
         if (Ctx::kFrame && tw_split) fft_batch_split<false, Ctx, T>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx_off);
-        else fft_batch<false>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
+        else fft_batch<false, GEN>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
         for (int e = ctx.tid; e < total; e += ctx.nt) {
             const int p = e >> g.lg_hx, k = e & (g.hx - 1);
             const cplx<T>* a = ws + p * g.rowstride;
             cplx<T> A, B;
             if (k == 0) {
-                const cplx<T> z0 = a[ppx[0]], zh = a[ppx[g.hx]];
+                const cplx<T> z0 = a[ppx[0]], zh = (!GEN || g.nyq >= 0) ? a[ppx[GEN ? g.nyq : g.hx]] : cmake<T>(0, 0);
                 A = cmake<T>(z0.re + z0.re, zh.re + zh.re);
                 B = cmake<T>(z0.im + z0.im, zh.im + zh.im);
-            } else {
-                const cplx<T> zk = a[ppx[k]], zm = a[ppx[g.nx - k]];
+            } else if (!GEN || k <= g.kmax) {
+                const cplx<T> zk = a[ppx[k]], zm = a[ppx[(GEN ? g.nmir : g.nx) - k]];
                 A = cmake<T>(zk.re + zm.re, zk.im - zm.im);
                 B = cmake<T>(zk.im + zm.im, zm.re - zk.re);
+            } else {
+                A = B = cmake<T>(0, 0);
             }
             const size_t row = (size_t)(r0 + 2 * (pair0 + p));
             spec[spec_idx<Ctx::kFrame>((int)row, k, g.lg_ny, g.lg_cp, g.hx)] = A;
@@ -173,7 +183,7 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
 // tf: [hx + 1][ny] complex in column-workspace position order (written by CONV_MAKE_TF);
 // row 0 = kx 0, rows 1..hx-1 = kx, row hx = kx nx/2.  Not inlined: it does not depend on the
 // producer / consumer, so all convolutions of the solver share one copy of the code.
-template <class Ctx, typename T>
+template <bool GEN, class Ctx, typename T>
 BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, unsigned twy_off, int tw_split, cplx<T>* spec, cplx<T>* tf, int mode) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     constexpr int U = 8;
@@ -181,6 +191,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
     g.ny = gp->ny; g.nx = gp->nx; g.hx = gp->hx; g.lg_ny = gp->lg_ny; g.lg_col_tile = gp->lg_col_tile; g.col_tile = gp->col_tile; g.lg_cp = gp->lg_cp;
     g.colstride = gp->colstride; g.cols_per_cta = gp->cols_per_cta;
     const FftPlan& py = gp->py;
+    const int ney = GEN ? fft_len(gp->py) : g.ny, nex = GEN ? fft_len(gp->px) : g.nx;     // transform lengths (== ny, nx unless an axis is a dense DFT)
     const int c0 = ctx.rank * g.cols_per_cta;
     const int ps = gp->py.pad_shift;
     const int ntiles = g.cols_per_cta / g.col_tile;
@@ -208,19 +219,19 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
         }
         ctx.sync();
         if (Ctx::kFrame && tw_split) fft_batch_split<false, Ctx, T>(ctx, ws_off, ct, g.colstride, py, twy_off);
-        else fft_batch<false>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
+        else fft_batch<false, GEN>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
         if (mode == CONV_MAKE_TF) {
             // column FFT of 2*A holds 2*TF; store TF * 0.5/(nx ny)
-            const T sc = (T)0.25 / ((T)g.nx * (T)g.ny);
+            const T sc = (T)0.25 / ((T)nex * (T)ney);
             for (int e = ctx.tid; e < (ct << g.lg_ny); e += ctx.nt) {
                 const int cl = e >> g.lg_ny, p = e & (g.ny - 1);
                 if (cc0 + cl == 0) continue;
                 tf[(size_t)(cc0 + cl) * g.ny + p] = cscale(ws[cl * g.colstride + fpad(p, ps)], sc);
             }
             if (cc0 == 0) {
-                const T sp = (T)0.0625 / ((T)g.nx * (T)g.ny);   // (C0 = 4 TF0) * 0.25/(nx ny)
-                for (int ky = ctx.tid; ky <= (g.ny >> 1); ky += ctx.nt) {
-                    const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, (g.ny - ky) & (g.ny - 1));
+                const T sp = (T)0.0625 / ((T)nex * (T)ney);   // (C0 = 4 TF0) * 0.25/(nx ny)
+                for (int ky = ctx.tid; ky <= (ney >> 1); ky += ctx.nt) {
+                    const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, GEN ? (ky ? ney - ky : 0) : ((g.ny - ky) & (g.ny - 1)));
                     const cplx<T> za = ws[fpad(pa, ps)], zb = ws[fpad(pb, ps)];
                     const cplx<T> c0v = cmake<T>(za.re + zb.re, za.im - zb.im);          // za + conj(zb)
                     const cplx<T> chv = cmake<T>(za.im + zb.im, zb.re - za.re);          // -i (za - conj(zb))
@@ -255,8 +266,8 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
             for (; e0 < mtotal; e0 += ctx.nt) mul_one(e0, tf[(size_t)(cc0 + (e0 >> g.lg_ny)) * g.ny + (e0 & (g.ny - 1))]);
         }
         if (cc0 == 0) {
-            for (int ky = ctx.tid; ky <= (g.ny >> 1); ky += ctx.nt) {
-                const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, (g.ny - ky) & (g.ny - 1));
+            for (int ky = ctx.tid; ky <= (ney >> 1); ky += ctx.nt) {
+                const int pa = pos_of_freq(py, ky), pb = pos_of_freq(py, GEN ? (ky ? ney - ky : 0) : ((g.ny - ky) & (g.ny - 1)));
                 cplx<T> t0a = tf[pa], tha = tf[(size_t)g.hx * g.ny + pa], t0b = tf[pb], thb = tf[(size_t)g.hx * g.ny + pb];
                 const cplx<T> za = ws[fpad(pa, ps)], zb = ws[fpad(pb, ps)];
                 const cplx<T> c0a = cmake<T>(za.re + zb.re, za.im - zb.im);
@@ -271,8 +282,8 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
         }
         ctx.sync();
         if (Ctx::kFrame && tw_split) fft_batch_split<true, Ctx, T>(ctx, ws_off, ct, g.colstride, py, twy_off);
-        else fft_batch<true>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
-        if (gp->wrap_ny > 0) {                            // wrapped plan: fold the linear result along the rows, z[i] += z[i + n]
+        else fft_batch<true, GEN>(ctx, ws_off, ct, g.colstride, py, twy, twy_off);
+        if (GEN && gp->wrap_ny > 0) {                            // wrapped plan: fold the linear result along the rows, z[i] += z[i + n]
             const int wn = gp->wrap_ny;
             for (int e = ctx.tid; e < ct * wn; e += ctx.nt) {
                 const int cl = e / wn, row = e - cl * wn;
@@ -290,13 +301,14 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 }
 
 // Consumer: In fetch(i); void apply(i, In, V2 value) for the slab pixel pair (i, i + 1).
-// WRAP: the geometry may ask for the column fold of a wrapped plan (value(c) = z[c] + z[c + wrap_nx] for c < wrap_nx).
+// WRAP: the geometry may ask for the column fold of a wrapped plan (value(c) = z[c] + z[c + wrap_nx] for c < wrap_nx) or
+// for a dense row transform (the GEN features of row_geom).
 template <int U, bool WRAP = false, class Ctx, typename T, class Fetch, class Apply>
 BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
     constexpr int UL = 4;
-    const RowGeom g = row_geom(gg);
+    const RowGeom g = row_geom<WRAP>(gg);
     const FftPlan& px = gg.px;
     const int r0 = ctx.rank * g.rows_per_cta;
     const int ps = g.ps;
@@ -310,10 +322,10 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 cplx<T>* a = ws + (e >> g.lg_hx) * g.rowstride;
                 if (k == 0) {
                     a[ppx[0]] = cmake<T>(A.re, B.re);
-                    a[ppx[g.hx]] = cmake<T>(A.im, B.im);
-                } else {
+                    if (!WRAP || g.nyq >= 0) a[ppx[WRAP ? g.nyq : g.hx]] = cmake<T>(A.im, B.im);
+                } else if (!WRAP || k <= g.kmax) {
                     a[ppx[k]] = cmake<T>(A.re - B.im, A.im + B.re);
-                    a[ppx[g.nx - k]] = cmake<T>(A.re + B.im, B.re - A.im);
+                    a[ppx[(WRAP ? g.nmir : g.nx) - k]] = cmake<T>(A.re + B.im, B.re - A.im);
                 }
             };
             int e0 = ctx.tid;
@@ -336,7 +348,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
         }
         ctx.sync();
         if (Ctx::kFrame && tw_split) fft_batch_split<true, Ctx, T>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx_off);
-        else fft_batch<true>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
+        else fft_batch<true, WRAP>(ctx, ws_off, g.row_tile_pairs, g.rowstride, px, twx, twx_off);
         {
             int e0 = ctx.tid;
             for (; U > 1 && e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {

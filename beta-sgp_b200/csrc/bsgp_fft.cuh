@@ -25,12 +25,19 @@ struct FftPlan {
     int log2r[6];   // log2 of the radix of each forward stage
     int pad_shift;  // log2 of the last radix
     int plen;       // padded length: n + (n >> pad_shift)
+    int dft_n;      // 0: radix stages over all n slots.  Otherwise the transform is a DENSE DFT of length dft_n <= n over
+                    // slots [0, dft_n), frequencies in natural order (small sides that are not a power of two, see
+                    // dense_dft_batch); the slots beyond keep whatever they hold
 };
+
+// transform length, as opposed to the number of workspace slots pl.n
+BSGP_DEV int fft_len(const FftPlan& pl) { return pl.dft_n ? pl.dft_n : pl.n; }
 
 BSGP_DEV int fpad(int i, int ps) { return i + (i >> ps); }
 
 // position (unpadded) of frequency k after the forward stages
 BSGP_DEV int pos_of_freq(const FftPlan& pl, int k) {
+    if (pl.dft_n) return k;
     int p = 0, lg = pl.log2n;
     for (int s = 0; s < pl.nstages; ++s) {
         lg -= pl.log2r[s];
@@ -166,14 +173,108 @@ BSGP_DEV void run_stages(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const Fft
 
 constexpr unsigned kNoSmem = 0xffffffffu;
 
+// ---------------------------------------------------------------------------------------------
+// Dense DFT for short transforms whose length is not a power of two (the reference's 31 x 31 cut-outs,
+// application_sgp_star_stamps.py:24,58): X[k] = sum_j x[j] w^(j k), w = exp(-+2 pi i / n), n = pl.dft_n <= 32, straight
+// from the table tw[m] = exp(-2 pi i m / n) (the exponent j k mod n is carried incrementally, so every twiddle is an
+// exact table entry).  In place like the radix stages: every thread first accumulates its outputs in registers, one
+// barrier, then stores them.  n^2 complex multiply-adds per transform instead of ~n log n, but the image
+// keeps its own size: all per-image arrays of a 31 x 31 solve stay resident in shared memory, where the alternative
+// (linear convolution on a 64 x 64 grid and a fold, "wrapped plans") works on arrays four times as large.
+// Ends with a barrier.
+// ---------------------------------------------------------------------------------------------
+// One task = one transform f and one frequency k <= n / 2; it delivers X[k] and X[n - k] from the same products:
+//   C = sum_j x[j] cos(2 pi j k / n),  S = sum_j x[j] sin(2 pi j k / n)   (complex x: four real multiply-adds per j)
+//   forward X[k] = C - i S, X[n - k] = C + i S;  inverse (unnormalised) the other way round.
+// R = tasks per thread (compile time, so the accumulators stay in registers); a slot beyond the last task repeats it.
+template <bool INV, int R, class Ctx, typename T>
+BSGP_DEV void dense_dft_tasks(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, int n, int ps, const cplx<T>* tw) {
+    const int per = (n >> 1) + 1, total = nfft * per;
+    cplx<T> C[R], S[R];
+    cplx<T>* src[R];
+    int kk[R], idx[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        int t = ctx.tid + u * ctx.nt;
+        t = t < total ? t : total - 1;                  // clamped, not guarded: the tile stays in registers
+        const int f = t / per;
+        kk[u] = t - f * per; idx[u] = 0;
+        src[u] = ws + f * fstride;
+        C[u] = S[u] = cmake<T>(0, 0);
+    }
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const int pj = fpad(j, ps);
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const cplx<T> v = src[u][pj], w = tw[idx[u]];        // w = (cos, -sin)
+            C[u].re += v.re * w.re; C[u].im += v.im * w.re;
+            S[u].re -= v.re * w.im; S[u].im -= v.im * w.im;
+            idx[u] += kk[u];
+            idx[u] = idx[u] >= n ? idx[u] - n : idx[u];
+        }
+    }
+    ctx.sync();
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        if (ctx.tid + u * ctx.nt < total) {
+            // C - i S = (C.re + S.im, C.im - S.re),  C + i S = (C.re - S.im, C.im + S.re)
+            const cplx<T> lo = cmake<T>(C[u].re + S[u].im, C[u].im - S[u].re), hi = cmake<T>(C[u].re - S[u].im, C[u].im + S[u].re);
+            src[u][fpad(kk[u], ps)] = INV ? hi : lo;
+            if (kk[u] != 0 && 2 * kk[u] != n) src[u][fpad(n - kk[u], ps)] = INV ? lo : hi;
+        }
+    }
+    ctx.sync();
+}
+
+template <bool INV, class Ctx, typename T>
+BSGP_DEV void dense_dft_batch(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw) {
+    const int n = pl.dft_n, ps = pl.pad_shift;
+#ifdef BSGP_HOST_EMUL
+    // one emulated thread: plain out-of-place sums per transform
+    cplx<T> tmp[64];
+    for (int f = 0; f < nfft; ++f) {
+        cplx<T>* a = ws + f * fstride;
+        for (int k = 0; k < n; ++k) {
+            cplx<T> acc = cmake<T>(0, 0);
+            int idx = 0;
+            for (int j = 0; j < n; ++j) {
+                const cplx<T> v = a[fpad(j, ps)], w = tw[idx];
+                acc = cadd(acc, INV ? cmulc(v, w) : cmul(v, w));
+                idx += k; if (idx >= n) idx -= n;
+            }
+            tmp[k] = acc;
+        }
+        for (int k = 0; k < n; ++k) a[fpad(k, ps)] = tmp[k];
+    }
+#else
+    const int total = nfft * ((n >> 1) + 1);
+    if (total <= ctx.nt) dense_dft_tasks<INV, 1>(ctx, ws, nfft, fstride, n, ps, tw);
+    else if (total <= 2 * ctx.nt) dense_dft_tasks<INV, 2>(ctx, ws, nfft, fstride, n, ps, tw);
+    else {
+        // more tasks than two per thread (narrow CTAs): groups of whole transforms, so that no group overwrites the inputs
+        // of a later one (a transform has at most 17 tasks; every CTA of this library has at least 128 threads)
+        const int per = (n >> 1) + 1, fpg = (2 * ctx.nt) / per;
+        for (int f0 = 0; f0 < nfft; f0 += fpg)
+            dense_dft_tasks<INV, 2>(ctx, ws + f0 * fstride, nfft - f0 < fpg ? nfft - f0 : fpg, fstride, n, ps, tw);
+    }
+#endif
+}
+
 // nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout), ws = shared memory at byte
 // offset ws_off.
 // Ends with a barrier.
 // Not inlined: the solver runs five convolutions, all sharing one copy of each direction.
 // tw_off: byte offset of the full twiddle table in shared memory (kNoSmem: read it through the generic pointer tw).
-template <bool INV, class Ctx, typename T>
+// GEN: the plan may ask for a dense DFT instead (embedded plans only, see row_geom in bsgp_conv.cuh).
+template <bool INV, bool GEN = false, class Ctx, typename T>
 BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
+    if (GEN && pl.dft_n) {
+        if (tw_off != kNoSmem) dense_dft_batch<INV>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
+        else dense_dft_batch<INV>(ctx, ws, nfft, fstride, pl, tw);
+        return;
+    }
     if (tw_off != kNoSmem) run_stages<INV, false>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
     else run_stages<INV, false>(ctx, ws, nfft, fstride, pl, tw);
 }

@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             };
             auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
+            conv_rows_forward<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+            conv_cols<true>(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
             T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
             const T* s0 = src + (size_t)r0 * nx;
@@ -87,9 +87,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_kernel(const ConvArgs<T> a, 
             auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
             auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
+            conv_rows_forward<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            conv_cols<true>(ctx, gs, off_ws, a.twy, kNoSmem, 0, spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
             conv_rows_inverse<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, spec, cf, ca);
         }
@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
             };
             auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
+            conv_rows_forward<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
+            conv_cols<true>(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (size_t)img * a.tf_stride, CONV_MAKE_TF);
         } else {
             T* dst = a.out + (size_t)img * npix + (size_t)r0 * nx;
             const T* s0 = src + (size_t)r0 * nx;
@@ -133,9 +133,9 @@ __global__ void __launch_bounds__(512, 1) bsgp_conv_frame_kernel(const ConvArgs<
             auto cf = [&](int) { In1<T> r; r.a = mk2((T)0, (T)0); return r; };
             auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(dst, i, v); };
             ctx.sync();
-            conv_rows_forward<2>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
+            conv_rows_forward<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, pf, pe);
             ctx.cluster_sync();
-            conv_cols(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
+            conv_cols<true>(ctx, gs, off_ws, a.twy, kNoSmem, 0, a.spec, a.tf + (a.n_psf > 1 ? (size_t)img * a.tf_stride : 0), a.mode);
             ctx.cluster_sync();
             conv_rows_inverse<2, true>(ctx, g, off_ws, a.twx, kNoSmem, 0, off_ppx, a.spec, cf, ca);
         }
@@ -433,10 +433,10 @@ template <typename T> static const void* conv_frame_kernel_ptr() { return (const
 
 template <typename T> static int alloc_tables(bsgp_plan* p) {
     std::vector<cplx<T>> tw;
-    make_twiddles<T>(p->nx, tw);
+    make_twiddles<T>(p->nx, tw, p->g.px.dft_n);
     CU(cudaMalloc(&p->twx, tw.size() * sizeof(cplx<T>)));
     CU(cudaMemcpy(p->twx, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
-    make_twiddles<T>(p->ny, tw);
+    make_twiddles<T>(p->ny, tw, p->g.py.dft_n);
     CU(cudaMalloc(&p->twy, tw.size() * sizeof(cplx<T>)));
     CU(cudaMemcpy(p->twy, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
     return BSGP_OK;
@@ -537,11 +537,13 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     }
     size_t ws_limit = (minb >= 4 ? 38 : 76) * 1024;
     if (const char* e = getenv("BSGP_WS_KB")) { const int v = atoi(e); if (v >= 8 && v <= 200) ws_limit = (size_t)v * 1024; }
-    bool ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes);
+    // short sides that are not a power of two: dense DFT of the image's own length on the first slots of the grid (bsgp_wrap.h)
+    const int dny = p->ny != p->img_ny ? dense_len(p->img_ny) : 0, dnx = p->nx != p->img_nx ? dense_len(p->img_nx) : 0;
+    bool ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes, dny, dnx);
     if (!ok && p->want_threads <= 0) {
         // one transform does not fit the small workspace (sides >= 4096): fall back to one big CTA per SM
         threads = 512; minb = 1; ws_limit = 160 * 1024;
-        ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes);
+        ok = make_geom(p->ny, p->nx, G, sizeof(cplx<T>), ws_limit, &p->g, &p->ws_bytes, dny, dnx);
     }
     if (!ok) return fail(BSGP_E_SHAPE, "unsupported shape %dx%d for cluster size %d (power-of-two sides >= 16 required)", p->ny, p->nx, G);
     p->threads = threads;
@@ -615,8 +617,8 @@ static int plan_setup(bsgp_plan* p) {
     CU(cudaSetDevice(p->device));
     const int rc = p->dtype == BSGP_F64 ? plan_setup_t<double>(p) : plan_setup_t<float>(p);
     if (rc) return rc;
-    p->g.wrap_ny = p->ny != p->img_ny ? p->img_ny : 0;
-    p->g.wrap_nx = p->nx != p->img_nx ? p->img_nx : 0;
+    p->g.wrap_ny = (p->ny != p->img_ny && !p->g.py.dft_n) ? p->img_ny : 0;      // fold widths; a dense axis is circular by itself
+    p->g.wrap_nx = (p->nx != p->img_nx && !p->g.px.dft_n) ? p->img_nx : 0;
     return BSGP_OK;
 }
 

@@ -15,7 +15,7 @@ inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // Stage radices (2, 4 or 8: a radix-8 butterfly of complex doubles fits a 128-register thread): every
 // stage has an in-block stride >= 8 (conflict-free 16-byte quarter-warp access) except the last,
 // whose radix (8) sets the padding period.
-inline bool make_fft_plan(int n, FftPlan* pl) {
+inline bool make_fft_plan(int n, FftPlan* pl, int dft_n = 0) {
     static const int table[16][6] = {
         {0}, {0}, {0},
         {3, 0},              // 8
@@ -32,7 +32,9 @@ inline bool make_fft_plan(int n, FftPlan* pl) {
         {2, 3, 3, 3, 3, 0},  // 16384
         {3, 3, 3, 3, 3, 0}}; // 32768
     if (!is_pow2(n) || n < 8 || n > 32768) return false;
+    if (dft_n < 0 || dft_n > n || dft_n > 64) return false;
     pl->n = n;
+    pl->dft_n = dft_n;
     pl->log2n = ilog2(n);
     int ns = 0;
     for (int s = 0; s < 6; ++s) pl->log2r[s] = 0;
@@ -50,7 +52,22 @@ inline bool make_fft_plan(int n, FftPlan* pl) {
 }
 
 // W_n^k = exp(-2 pi i k / n), k in [0, n), computed in long double and rounded once.
-template <typename T> inline void make_twiddles(int n, std::vector<cplx<T>>& tw) {
+// A dense transform of length dft_n < n keeps the table size n (the kernels copy n entries to shared memory) and
+// fills its first dft_n entries with W_dft_n^k.
+template <typename T> inline void make_twiddles(int n, std::vector<cplx<T>>& tw, int dft_n = 0) {
+    if (dft_n) {
+        tw.assign(n, cplx<T>{(T)0, (T)0});
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int k = 0; k < dft_n; ++k) {
+            const long double ang = two_pi * (long double)k / (long double)dft_n;
+            tw[k].re = (T)cosl(ang);
+            tw[k].im = (T)(-sinl(ang));
+        }
+        tw[0].re = 1; tw[0].im = 0;
+        if (dft_n % 2 == 0) { tw[dft_n / 2].re = -1; tw[dft_n / 2].im = 0; }
+        if (dft_n % 4 == 0) { tw[dft_n / 4].re = 0; tw[dft_n / 4].im = -1; tw[3 * dft_n / 4].re = 0; tw[3 * dft_n / 4].im = 1; }
+        return;
+    }
     tw.resize(n);
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int k = 0; k < n; ++k) {
@@ -67,10 +84,12 @@ template <typename T> inline void make_twiddles(int n, std::vector<cplx<T>>& tw)
 
 // Geometry for a cluster of G CTAs and a shared-memory FFT workspace of at most ws_limit bytes.
 // Returns false if the shape cannot be handled.
+// dft_ny / dft_nx: 0, or the length of the dense DFT that replaces the radix transform along that axis (bsgp_fft.cuh).
 inline bool make_geom(int ny, int nx, int G, size_t elem_bytes /* sizeof(cplx<T>) */, size_t ws_limit, ConvGeom* g,
-                      size_t* ws_bytes) {
+                      size_t* ws_bytes, int dft_ny = 0, int dft_nx = 0) {
     if (!is_pow2(ny) || !is_pow2(nx) || ny < 16 || nx < 16) return false;
-    if (!make_fft_plan(nx, &g->px) || !make_fft_plan(ny, &g->py)) return false;
+    if (!make_fft_plan(nx, &g->px, dft_nx) || !make_fft_plan(ny, &g->py, dft_ny)) return false;
+    if ((dft_ny || dft_nx) && G != 1) return false;          // dense transforms: small images, one CTA each
     g->ny = ny; g->nx = nx; g->hx = nx / 2;
     g->lg_nx = ilog2(nx); g->lg_ny = ilog2(ny); g->lg_hx = g->lg_nx - 1;
     g->G = G;

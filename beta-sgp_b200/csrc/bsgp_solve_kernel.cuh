@@ -45,7 +45,14 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
         S->geom = a.g;
         S->ppx_off = sp.off_ppx;
         S->ws_off = sp.off_ws;
-        S->spec = a.spec + (size_t)cluster_id * a.spec_stride;
+        // One CTA per image with d_tf resident (stamps): the half-spectrum exchange buffer (ny x nx/2 complex = one image
+        // array) BORROWS the d_tf array instead of living in global memory.  With one workspace tile per pass every
+        // producer has read all of its inputs before the first spectrum element is written, and every consumer has moved
+        // the whole spectrum into the workspace before it stores its first output; d_tf itself is dead across every
+        // convolution: it is written by the consumer of A(d) (ph_ri_trial), read by the line search and, for the last
+        // time, by the producer of the accepted step's A^T (ph_rf_grad).
+        const bool spec_in_dtf = a.g.G == 1 && ((a.resident_mask >> B_DTF) & 1) && 2 * a.g.row_tile_pairs == a.g.ny && a.g.col_tile == a.g.hx;
+        S->spec = spec_in_dtf ? reinterpret_cast<cplx<T>*>(buf[B_DTF]) : a.spec + (size_t)cluster_id * a.spec_stride;
         S->twx = a.twx; S->twy = a.twy;
         S->twx_off = sp.tw_smem ? sp.off_twx : kNoSmem;
         S->twy_off = sp.tw_smem ? sp.off_twy : kNoSmem;

@@ -347,12 +347,12 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE R2 ph_err0(Ctx ctx, cons
 // output divisor: 1 for the circular operator, the kernel-weight constant of the zero-padded one.
 // -------------------------------------------------------------------------------------------------
 // producer: plain copy of x (which = 0) or gn (which = 1); both are zero in the padding
-template <typename T, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const ImgState<T>* S, int which) {
+template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_rf_copy(Ctx ctx, const ImgState<T>* S, int which) {
     ctx.sync();
     const T* src = which ? S->gn : S->x;
     auto pf = [&](int i) { In1<T> r; r.a = ld2(src, i); return r; };
     auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-    conv_rows_forward<2>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<2, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer of A(x): x_tf, objective terms, gradient cache                sgp.py:260-265 / 702-709
@@ -398,7 +398,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE void ph_rf_grad(Ctx ctx,
         return mk2(inside<MK>(R, i) ? nmul(in.e.x, ndiv(in.c.x, nadd(xt.x, in.d.x))) : (T)0,
                    inside<MK>(R, i + 1) ? nmul(in.e.y, ndiv(in.c.y, nadd(xt.y, in.d.y))) : (T)0);
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
 }
 
 // consumer: g = 1 - w (KL) or den^(beta-1) - w                            sgp.py:262 / 705
@@ -512,7 +512,7 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_rf_dir(Ctx ctx
         st2(dbuf, i, d);
         return d;
     };
-    conv_rows_forward<1>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
+    conv_rows_forward<1, MK>(ctx, S->geom, S->ws_off, S->twx, S->twx_off, S->tw_split, S->ppx_off, S->spec, pf, pe);
     return gd;
 }
 
@@ -657,9 +657,9 @@ template <typename T, class Ctx> BSGP_NOINLINE void ph_store_out(Ctx ctx, const 
 }
 
 // the two column passes between a producer and a consumer
-template <typename T, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgState<T>* S, cplx<T>* tf, int mode) {
+template <typename T, bool MK, class Ctx> BSGP_DEV void conv_middle(Ctx& ctx, const ImgState<T>* S, cplx<T>* tf, int mode) {
     ctx.cluster_sync();
-    conv_cols(ctx, &S->geom, S->ws_off, S->twy, S->twy_off, S->tw_split, S->spec, tf, mode);
+    conv_cols<MK>(ctx, &S->geom, S->ws_off, S->twy, S->twy_off, S->tw_split, S->spec, tf, mode);
     ctx.cluster_sync();
 }
 
@@ -888,8 +888,8 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
 
     if (W->status == BSGP_ST_OK) {
         // ---------------------------------------------------------------- x_tf = A(x), objective (:260-265)
-        ph_rf_copy<T>(ctx, S, 0);
-        conv_middle<T>(ctx, S, S->tf, CONV_TF);
+        ph_rf_copy<T, MK>(ctx, S, 0);
+        conv_middle<T, MK>(ctx, S, S->tf, CONV_TF);
         double acc[3];
         {
             const R3 o = BSGP_DISPATCH_KIND(W->dk, ph_ri_obj0_k, ctx, S, W->dk);
@@ -900,11 +900,11 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
         W->fv = objective_value(W->dk, acc, W->s1, W->flux, W->npix_d);
         // ---------------------------------------------------------------- gradient
         ph_rf_grad<T, MK>(ctx, S, W->dk.kind, (T)0, F_FIRST);
-        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        conv_middle<T, MK>(ctx, S, S->tf_at, mode_at);
         ph_ri_grad0<T, MK>(ctx, S, W->dk.kind);
         // ---------------------------------------------------------------- scaling-matrix bounds (:268-273)
-        ph_rf_copy<T>(ctx, S, 1);
-        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        ph_rf_copy<T, MK>(ctx, S, 1);
+        conv_middle<T, MK>(ctx, S, S->tf_at, mode_at);
         const R2 lh = ph_ri_bounds<T, MK>(ctx, S, W->flux);
         double lo = lh.a, hi = lh.b;
         allreduce_fn<1, 1>(ctx, &lo);
@@ -976,7 +976,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
             double sums[4];   // [0..2] objective terms, [3] gd
             sums[3] = ph_rf_dir<T, MK>(ctx, S, W->al, W->lam_proj, W->lam_pending, W->flags);
             W->pending = 0;
-            conv_middle<T>(ctx, S, S->tf, CONV_TF);
+            conv_middle<T, MK>(ctx, S, S->tf, CONV_TF);
             {
                 const R3 o = BSGP_DISPATCH_KIND(W->dk, ph_ri_trial_k, ctx, S, W->dk);
                 sums[0] = o.a; sums[1] = o.b; sums[2] = o.c;
@@ -1014,7 +1014,7 @@ BSGP_DEV void solve_image(Ctx& ctx, const SolveArgs<T>& a, ImgState<T>* S, T* co
 
         // ---- accept: x_tf, new gradient through A^T, BB sums (:337-347, 355-365, 402); x itself is updated lazily
         ph_rf_grad<T, MK>(ctx, S, W->dk.kind, (T)W->lam, 0);
-        conv_middle<T>(ctx, S, S->tf_at, mode_at);
+        conv_middle<T, MK>(ctx, S, S->tf_at, mode_at);
         R7 bbr = ph_ri_bb<T, MK>(ctx, S, (T)W->lam, W->dk.kind);
         allreduce_fn<0, 7>(ctx, bbr.v);
         W->X_is_ones = 0;

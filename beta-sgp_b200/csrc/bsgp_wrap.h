@@ -21,10 +21,21 @@
 namespace bsgp {
 
 constexpr int kMaxSide = 8192;
+constexpr int kMaxDense = 32;
+
+// Short sides that are not a power of two (n <= 32: the reference's 31 x 31 cut-outs) do not wrap: they keep a grid of
+// side 16 or 32 >= n and their transform is a dense DFT of length n over the first n slots (bsgp_fft.cuh,
+// dense_dft_batch), i.e. the circular operator itself - no fold, and arrays of the image's own size.
+// dense_len(n) is that length, 0 for every other side.
+BSGP_HD int dense_len(int n) {
+    if (n >= 16 && (n & (n - 1)) == 0) return 0;
+    return n <= kMaxDense ? n : 0;
+}
 
 // FFT grid side for an image side n; > kMaxSide means unsupported
 BSGP_HD int wrap_grid_side(int n) {
     if (n >= 16 && n <= kMaxSide && (n & (n - 1)) == 0) return n;
+    if (dense_len(n)) return n <= 16 ? 16 : 32;
     int P = 16;
     while (P < 2 * n - 1 && P <= kMaxSide) P *= 2;
     return P;
@@ -33,7 +44,8 @@ BSGP_HD int wrap_grid_side(int n) {
 // Kernel image handed to CONV_MAKE_TF for a wrapped plan.  CONV_MAKE_TF computes fftn(fftshift_P(g)) on the grid, so
 // g[(j + P/2) mod P] = k[j] puts kernel value k[j] at grid index j: k = h for A, k = h~ for A^T.  Returns false where
 // g is zero; otherwise (*sr, *sc) is the pixel of the caller's PSF that belongs at grid position (r, c).  An axis whose
-// grid side equals the image side (a power of two) reduces to g = psf (A) or the index-reversed psf (A^T).
+// grid side equals the image side (a power of two) reduces to g = psf (A) or the index-reversed psf (A^T).  A dense axis
+// uses the same placement: its transform sees k on slots [0, n) and computes the length-n DFT of it.
 BSGP_HD bool wrap_psf_source(int r, int c, int ny, int nx, int iny, int inx, int adjoint, int* sr, int* sc) {
     int jr = (r + ny - (ny >> 1)) % ny, jc = (c + nx - (nx >> 1)) % nx;
     if (jr >= iny || jc >= inx) return false;

@@ -41,10 +41,10 @@ template <typename T, class C = HostCtx> struct HostPlan {
     std::vector<unsigned char> arena;      // emulated dynamic shared memory: [position table][workspace]
     unsigned ws_off = 0, ppx_off = 0;
     void bind() { g_emul_smem = arena.data(); }
-    bool init(int ny, int nx, int G, size_t ws_limit) {
-        if (!make_geom(ny, nx, G, sizeof(cplx<T>), ws_limit, &g, &ws_bytes)) return false;
-        make_twiddles<T>(nx, twx);
-        make_twiddles<T>(ny, twy);
+    bool init(int ny, int nx, int G, size_t ws_limit, int dft_ny = 0, int dft_nx = 0) {
+        if (!make_geom(ny, nx, G, sizeof(cplx<T>), ws_limit, &g, &ws_bytes, dft_ny, dft_nx)) return false;
+        make_twiddles<T>(nx, twx, dft_nx);
+        make_twiddles<T>(ny, twy, dft_ny);
         spec.assign((size_t)ny * g.hx, cmake<T>(0, 0));
         tf.assign((size_t)(g.hx + 1) * ny, cmake<T>(0, 0));
         ws_off = (unsigned)(((size_t)nx * sizeof(unsigned short) + 127) & ~(size_t)127);
@@ -67,8 +67,8 @@ template <typename T, class C = HostCtx> struct HostPlan {
                     In1<T> q; q.a = ld2(psf + (size_t)((r0 + row + ny / 2) & (ny - 1)) * nx, (c + nx / 2) & (nx - 1)); return q;
                 };
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
-                else conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), out.data(), CONV_MAKE_TF);
+                if (phase == 0) conv_rows_forward<2, true>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
+                else conv_cols<true>(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), out.data(), CONV_MAKE_TF);
             }
     }
     void apply(const T* x, T* y, int adjoint) {
@@ -82,8 +82,8 @@ template <typename T, class C = HostCtx> struct HostPlan {
                 auto pe = [&](int, const In1<T>& in) -> V2<T> { return in.a; };
                 auto cf = [&](int) { In1<T> q; q.a = mk2((T)0, (T)0); return q; };
                 auto ca = [&](int i, const In1<T>&, V2<T> v) { st2(y + off, i, v); };
-                if (phase == 0) conv_rows_forward<2>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
-                else if (phase == 1) conv_cols(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
+                if (phase == 0) conv_rows_forward<2, true>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), pf, pe);
+                else if (phase == 1) conv_cols<true>(ctx, &g, ws_off, twy.data(), kNoSmem, 0, spec.data(), tf.data(), adjoint ? CONV_CTF : CONV_TF);
                 else conv_rows_inverse<2, true>(ctx, g, ws_off, twx.data(), kNoSmem, 0, ppx_off, spec.data(), cf, ca);
             }
     }
@@ -99,8 +99,8 @@ template <typename T, class C = HostCtx> struct HostPlan {
                 }
             make_tf(k.data(), adj ? &tf_adj : nullptr);
         }
-        g.wrap_ny = ny != iny ? iny : 0;
-        g.wrap_nx = nx != inx ? inx : 0;
+        g.wrap_ny = (ny != iny && !g.py.dft_n) ? iny : 0;
+        g.wrap_nx = (nx != inx && !g.px.dft_n) ? inx : 0;
     }
 };
 
@@ -136,8 +136,8 @@ int emul_fft1d(int n, int nfft, const double* in, double* out, int inverse_after
         fft_batch_split<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw_off);
         if (inverse_after) fft_batch_split<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw_off);
     } else {
-        fft_batch<false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
-        if (inverse_after) fft_batch<true, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
+        fft_batch<false, false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
+        if (inverse_after) fft_batch<true, false, HostCtx, double>(ctx, 0u, nfft, stride, pl, tw.data(), tw_off);
     }
     for (int f = 0; f < nfft; ++f)
         for (int k = 0; k < n; ++k) {
@@ -163,7 +163,7 @@ int emul_conv_wrapped(int iny, int inx, int G, long long ws_limit, const double*
     const int ny = wrap_grid_side(iny), nx = wrap_grid_side(inx);
     if (ny > kMaxSide || nx > kMaxSide) return 2;
     HostPlan<double> pl;
-    if (!pl.init(ny, nx, G, (size_t)ws_limit)) return 1;
+    if (!pl.init(ny, nx, G, (size_t)ws_limit, ny != iny ? dense_len(iny) : 0, nx != inx ? dense_len(inx) : 0)) return 1;
     pl.make_tf_wrapped(psf, iny, inx);
     std::vector<double> xe((size_t)ny * nx), ye((size_t)ny * nx);
     embed(x, iny, inx, xe.data(), ny, nx);
@@ -234,7 +234,7 @@ int emul_solve_wrapped(int iny, int inx, const bsgp_params* params, const double
     const int ny = wrap_grid_side(iny), nx = wrap_grid_side(inx);
     if (ny > kMaxSide || nx > kMaxSide) return 2;
     HostPlan<double> pl;
-    if (!pl.init(ny, nx, 1, (size_t)1 << 30)) return 1;
+    if (!pl.init(ny, nx, 1, (size_t)1 << 30, ny != iny ? dense_len(iny) : 0, nx != inx ? dense_len(inx) : 0)) return 1;
     pl.make_tf_wrapped(psf, iny, inx);
     const size_t npix = (size_t)ny * nx;
     std::vector<double> work(NBUF * npix, 0.0), times(params->maxit + 1, 0.0), gne(npix), bke(npix), x0e(npix), obe(npix), xe(npix);

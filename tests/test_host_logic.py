@@ -269,8 +269,8 @@ def test_psf_model_file_parsing(tmp_path):
     assert row.shape == (5 + 12,) and np.array_equal(row[5:], g["file_values"][14:26])
 
 
-@pytest.mark.parametrize("ny,nx,G,ws", [(31, 31, 1, 1 << 20), (31, 31, 2, 1 << 20), (33, 20, 1, 1 << 20), (48, 48, 4, 1 << 20),
-                                        (5, 7, 1, 1 << 20), (32, 31, 1, 1 << 20), (31, 64, 2, 40 * 1024), (100, 75, 8, 72 * 1024),
+@pytest.mark.parametrize("ny,nx,G,ws", [(31, 31, 1, 1 << 20), (30, 30, 1, 1 << 20), (17, 24, 1, 1 << 20), (9, 12, 1, 1 << 20), (33, 20, 1, 1 << 20), (48, 48, 4, 1 << 20),
+                                        (5, 7, 1, 1 << 20), (32, 31, 1, 1 << 20), (31, 64, 1, 40 * 1024), (100, 75, 8, 72 * 1024),
                                         (375, 375, 8, 72 * 1024), (450, 450, 8, 160 * 1024)])
 def test_emulated_wrapped_convolution(ny, nx, G, ws):
     """Sides that are not powers of two (sgp.py:108-120 accepts any size; application_sgp_star_stamps.py:24 uses 31):
