@@ -107,8 +107,9 @@ template <class Ctx> BSGP_DEV void fill_pos_table(Ctx& ctx, const FftPlan& pl, u
 }
 
 // Producer: In fetch(i); V2 eval(i, In) for the slab pixel pair (i, i + 1), i = local_row * nx + col.
-template <int U, bool GEN = false, class Ctx, typename T, class Fetch, class Eval>
+template <int U_, bool GEN = false, class Ctx, typename T, class Fetch, class Eval>
 BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, cplx<T>* spec, Fetch& fetch, Eval& eval) {
+    constexpr int U = Ctx::kSmall ? 1 : U_;                  // small images: a thread has one or two steps per pass, batches would only be code
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
     const RowGeom g = row_geom<GEN>(gg);                     // scalars in registers; the FFT plan stays where it is
@@ -143,6 +144,7 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 row[fpad(c + 1, ps)] = cmake<T>(v0.y, v1.y);
             }
         }
+#pragma unroll 1
         for (; e0 < total; e0 += ctx.nt) {
             const int p = e0 >> g.lg_hx, c = 2 * (e0 & (g.hx - 1));
             const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
@@ -186,7 +188,7 @@ BSGP_DEV void conv_rows_forward(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
 template <bool GEN, class Ctx, typename T>
 BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const cplx<T>* twy, unsigned twy_off, int tw_split, cplx<T>* spec, cplx<T>* tf, int mode) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
-    constexpr int U = 8;
+    constexpr int U = Ctx::kSmall ? 1 : 8;
     struct { int ny, nx, hx, lg_ny, lg_col_tile, col_tile, colstride, cols_per_cta, lg_cp; } g;      // register copies
     g.ny = gp->ny; g.nx = gp->nx; g.hx = gp->hx; g.lg_ny = gp->lg_ny; g.lg_col_tile = gp->lg_col_tile; g.col_tile = gp->col_tile; g.lg_cp = gp->lg_cp;
     g.colstride = gp->colstride; g.cols_per_cta = gp->cols_per_cta;
@@ -201,7 +203,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
         const int total = g.ny << g.lg_col_tile;
         {
             int e0 = ctx.tid;
-            for (; e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
+            for (; U > 1 && e0 + (U - 1) * ctx.nt < total; e0 += ctx.nt * U) {
                 cplx<T> v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -214,6 +216,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
                     ws[(e & (ct - 1)) * g.colstride + fpad(e >> g.lg_col_tile, ps)] = v[u];
                 }
             }
+#pragma unroll 1
             for (; e0 < total; e0 += ctx.nt)
                 ws[(e0 & (ct - 1)) * g.colstride + fpad(e0 >> g.lg_col_tile, ps)] = spec[spec_idx<Ctx::kFrame>(e0 >> g.lg_col_tile, cc0 + (e0 & (ct - 1)), g.lg_ny, g.lg_cp, g.hx)];
         }
@@ -253,7 +256,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
                 }
             };
             int e0 = ctx.tid;
-            for (; e0 + (U - 1) * ctx.nt < mtotal; e0 += ctx.nt * U) {
+            for (; U > 1 && e0 + (U - 1) * ctx.nt < mtotal; e0 += ctx.nt * U) {
                 cplx<T> t[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -263,6 +266,7 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 #pragma unroll
                 for (int u = 0; u < U; ++u) mul_one(e0 + u * ctx.nt, t[u]);
             }
+#pragma unroll 1
             for (; e0 < mtotal; e0 += ctx.nt) mul_one(e0, tf[(size_t)(cc0 + (e0 >> g.lg_ny)) * g.ny + (e0 & (g.ny - 1))]);
         }
         if (cc0 == 0) {
@@ -303,11 +307,12 @@ BSGP_NOINLINE void conv_cols(Ctx ctx, const ConvGeom* gp, unsigned ws_off, const
 // Consumer: In fetch(i); void apply(i, In, V2 value) for the slab pixel pair (i, i + 1).
 // WRAP: the geometry may ask for the column fold of a wrapped plan (value(c) = z[c] + z[c + wrap_nx] for c < wrap_nx) or
 // for a dense row transform (the GEN features of row_geom).
-template <int U, bool WRAP = false, class Ctx, typename T, class Fetch, class Apply>
+template <int U_, bool WRAP = false, class Ctx, typename T, class Fetch, class Apply>
 BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, const cplx<T>* twx, unsigned twx_off, int tw_split, unsigned ppx_off, const cplx<T>* spec, Fetch& fetch, Apply& apply) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     const unsigned short* ppx = smem_at<unsigned short>(ppx_off);
-    constexpr int UL = 4;
+    constexpr int U = Ctx::kSmall ? 1 : U_;
+    constexpr int UL = Ctx::kSmall ? 1 : 4;
     const RowGeom g = row_geom<WRAP>(gg);
     const FftPlan& px = gg.px;
     const int r0 = ctx.rank * g.rows_per_cta;
@@ -329,7 +334,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                 }
             };
             int e0 = ctx.tid;
-            for (; e0 + (UL - 1) * ctx.nt < total; e0 += ctx.nt * UL) {
+            for (; UL > 1 && e0 + (UL - 1) * ctx.nt < total; e0 += ctx.nt * UL) {
                 cplx<T> A[UL], B[UL];
 #pragma unroll
                 for (int u = 0; u < UL; ++u) {
@@ -341,6 +346,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
 #pragma unroll
                 for (int u = 0; u < UL; ++u) tangle(e0 + u * ctx.nt, A[u], B[u]);
             }
+#pragma unroll 1
             for (; e0 < total; e0 += ctx.nt) {
                 const size_t row = (size_t)(r0 + 2 * (pair0 + (e0 >> g.lg_hx)));
                 tangle(e0, spec[spec_idx<Ctx::kFrame>((int)row, e0 & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)], spec[spec_idx<Ctx::kFrame>((int)row + 1, e0 & (g.hx - 1), g.lg_ny, g.lg_cp, g.hx)]);
@@ -372,6 +378,7 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
                     apply(i0 + g.nx, in1[u], mk2<T>(z0.im, z1.im));
                 }
             }
+#pragma unroll 1
             for (; e0 < total; e0 += ctx.nt) {
                 const int p = e0 >> g.lg_hx, c = 2 * (e0 & (g.hx - 1));
                 const int i0 = ((2 * (pair0 + p)) << g.lg_nx) + c;
@@ -389,8 +396,9 @@ BSGP_DEV void conv_rows_inverse(Ctx& ctx, const ConvGeom& gg, unsigned ws_off, c
 }
 
 // elementwise loop over pixel pairs with batched loads: In fetch(i) (loads only), body(i, In), i even
-template <int U, class Ctx, class Fetch, class Body>
+template <int U_, class Ctx, class Fetch, class Body>
 BSGP_DEV void pair_loop(Ctx& ctx, int n, Fetch& fetch, Body& body) {
+    constexpr int U = Ctx::kSmall ? 1 : U_;
     const int np = n >> 1;
     int q0 = ctx.tid;
     for (; U > 1 && q0 + (U - 1) * ctx.nt < np; q0 += ctx.nt * U) {  // full batches: no guards, the tile stays in registers (U == 1: the loop below is the same)
@@ -400,6 +408,7 @@ BSGP_DEV void pair_loop(Ctx& ctx, int n, Fetch& fetch, Body& body) {
 #pragma unroll
         for (int u = 0; u < U; ++u) body(2 * (q0 + u * ctx.nt), in[u]);
     }
+#pragma unroll 1
     for (; q0 < np; q0 += ctx.nt) {
         const auto in = fetch(2 * q0);
         body(2 * q0, in);

@@ -44,6 +44,7 @@ __device__ __forceinline__ unsigned map_to_rank(unsigned addr, int rank) {
 
 struct DeviceCtx {
     static constexpr bool kFrame = false;     // cluster mode: row-major exchange buffer, full twiddle tables
+    static constexpr bool kSmall = false;     // see DeviceCtxSmall
     int tid, nt, rank, G;
     SharedCtl* sh;
     int parity;        // bit 0: inbox half in use; bits 1, 2: phase of mbar[0], mbar[1]
@@ -125,6 +126,14 @@ struct DeviceCtx {
     __device__ __forceinline__ void allreduce_max(double& v) { allreduce(2, &v, 1); }
 };
 
+// The same context for images that live entirely in one CTA's shared memory (stamps: 32 x 32 pixels over 256 threads).  A
+// thread then has one or two steps per pass: the register-tile batches that hide HBM latency on large slabs would only
+// be code that is fetched and never looped over, and these kernels are bound by instruction fetch (the per-iteration code
+// of a stamp solve is several times the instruction cache).  kSmall compiles every pass as its plain loop.
+struct DeviceCtxSmall : DeviceCtx {
+    static constexpr bool kSmall = true;
+};
+
 // every CTA initialises its two transaction barriers (one arrival each: its own expect_tx); the first
 // next_item() cluster barrier publishes them before any peer can target them
 __device__ __forceinline__ void init_ctx_barriers(const DeviceCtx& c) {
@@ -155,6 +164,7 @@ __device__ __forceinline__ DeviceCtx make_ctx(SharedCtl* sh, int G) {
 // -------------------------------------------------------------------------------------------------
 struct GridCtx {
     static constexpr bool kFrame = true;      // frame mode: panel exchange buffer, two-level twiddle tables allowed
+    static constexpr bool kSmall = false;
     int tid, nt, rank, G;
     SharedCtl* sh;
     double* gpart;      // [2][G][kMaxK]

@@ -261,6 +261,93 @@ BSGP_DEV void dense_dft_batch(Ctx& ctx, cplx<T>* ws, int nfft, int fstride, cons
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same dense DFT on the fp64 tensor cores (mma.sync m8n8k4, DMMA).  A batch of nfft complex transforms of length n
+// is one real matrix product  Out[2 f + part][2 k + t] = sum_j In[2 f + part][j] * Wt[j][2 k + t]  with
+//   In[2 f + part][j] = re (part 0) or im (part 1) of element j of transform f   (M = 2 nfft rows, K = n),
+//   Wt[j][2 k + t]    = cos (t 0) or sin (t 1) of 2 pi j k / n, k <= n / 2         (N = 2 (n / 2 + 1) columns),
+// i.e. the sums C and S of dense_dft_tasks for every (f, k), re and im parts in neighbouring rows.  An 8 x 8 output tile
+// takes ceil(n / 4) DMMA instructions; the B operand comes from a table in shared memory that is laid out in fragment
+// order (fill_dense_table: one coalesced 8-byte load per lane and step), the A operand straight from the workspace.
+// A lane ends up with C and S of one (f, part, k); its partner for the other part is lane ^ 4, so one shuffle completes
+//   X[k] = C - i S = (Cr + Si, Ci - Sr),   X[n - k] = C + i S = (Cr - Si, Ci + Sr)      (forward; swapped for the inverse).
+// 31-point transforms: 16 tiles x 8 steps = 128 DMMA per batch of 16 transforms, against 256 threads x 31 steps x 14
+// instructions of the scalar version, and an eighth of its shared-memory traffic (ncu: the scalar version spent 36 % of
+// a 31 x 31 solve in this function at 60 % shared-memory pipe utilisation, 2.4 G bank-conflict wavefronts).
+// ---------------------------------------------------------------------------------------------
+constexpr int kDenseTilesPerWarp = 4;          // 16 tiles over the four warps of the narrowest CTA
+
+// fragment-order table for a grid of side ng (table of (ng / 8) x (ng / 4) x 32 doubles = 8 ng^2 bytes): entry
+// [(nt * (ng / 4) + s) * 32 + lane] = Wt[4 s + (lane & 3)][8 nt + (lane >> 2)], zero outside j < n, k <= n / 2
+template <class Ctx, typename T> BSGP_DEV void fill_dense_table(Ctx& ctx, int ng, int n, const cplx<T>* tw, double* dst) {
+    const int S = ng >> 2, total = (ng >> 3) * S * 32;
+    for (int e = ctx.tid; e < total; e += ctx.nt) {
+        const int lane = e & 31, s = (e >> 5) % S, nt = (e >> 5) / S;
+        const int j = 4 * s + (lane & 3), nn = 8 * nt + (lane >> 2), k = nn >> 1;
+        double v = 0.0;
+        if (j < n && 2 * k <= n) {
+            const cplx<T> w = tw[(j * k) % n];                  // (cos, -sin)
+            v = (nn & 1) ? -(double)w.im : (double)w.re;
+        }
+        dst[e] = v;
+    }
+}
+
+#ifndef BSGP_HOST_EMUL
+// Preconditions (checked by fft_batch): grid side pl.n = 16 or 32 with padding period 8 (pad_shift 3), nfft a multiple of 4,
+// whole warps, at most kDenseTilesPerWarp tiles per warp.  The step loop is unrolled over the grid's 8 (or 4) steps so that
+// every address is base + immediate: fpad(4 s + jl) = 4 s + jl + (s >> 1) for a padding period of 8.
+template <bool INV, class Ctx>
+BSGP_DEV void dense_dft_mma(Ctx& ctx, cplx<double>* ws, int nfft, int fstride, const FftPlan& pl, const double* tab) {
+    const int n = pl.dft_n;
+    const int lane = ctx.tid & 31, warp = ctx.tid >> 5, nwarps = ctx.nt >> 5;
+    const int per = (n >> 1) + 1;
+    const int lgNT = pl.log2n - 3, tiles = (nfft >> 2) << lgNT;          // 8 x 8 tiles: 4 frequencies (cos, sin) x 4 transforms (re, im); all of the table's column tiles
+    const int S = (n + 3) >> 2, Sfull = pl.n >> 2;
+    double* wsd = reinterpret_cast<double*>(ws);
+    const int part = (lane >> 2) & 1, jl = lane & 3;
+    double c0[kDenseTilesPerWarp], c1[kDenseTilesPerWarp];
+#pragma unroll
+    for (int i = 0; i < kDenseTilesPerWarp; ++i) {
+        c0[i] = 0.0; c1[i] = 0.0;
+        const int tile = warp + i * nwarps;                   // tile = nt + NT * mt
+        if (tile < tiles) {
+            const int mt = tile >> lgNT, nt = tile & ((1 << lgNT) - 1);
+            const double* arow = wsd + 2 * ((4 * mt + (lane >> 3)) * fstride + jl) + part;
+            const double* brow = tab + (nt * Sfull) * 32 + lane;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < S) {
+                    double a = arow[2 * (4 * s + (s >> 1))];
+                    a = (4 * s + jl < n) ? a : 0.0;           // a slot beyond the transform may hold anything
+                    const double b = brow[s * 32];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+                }
+            }
+        }
+    }
+    ctx.sync();                                               // every warp has read its inputs
+#pragma unroll
+    for (int i = 0; i < kDenseTilesPerWarp; ++i) {
+        const int tile = warp + i * nwarps;
+        if (tile < tiles) {                                   // warp-uniform
+            const int mt = tile >> lgNT, nt = tile & ((1 << lgNT) - 1);
+            const double other = __shfl_xor_sync(0xffffffffu, c1[i], 4);     // the S sum of the other part
+            const double lo = part ? c0[i] - other : c0[i] + other;
+            const double hi = part ? c0[i] + other : c0[i] - other;
+            const int k = 4 * nt + jl;
+            double* orow = wsd + 2 * ((4 * mt + (lane >> 3)) * fstride) + part;
+            if (k < per) {
+                orow[2 * fpad(k, 3)] = INV ? hi : lo;
+                if (k != 0 && 2 * k != n) orow[2 * fpad(n - k, 3)] = INV ? lo : hi;
+            }
+        }
+    }
+    ctx.sync();
+}
+#endif
+
 // nfft transforms of length pl.n, transform f at ws + f*fstride (padded layout), ws = shared memory at byte
 // offset ws_off.
 // Ends with a barrier.
@@ -271,8 +358,17 @@ template <bool INV, bool GEN = false, class Ctx, typename T>
 BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, const FftPlan& pl, const cplx<T>* tw, unsigned tw_off) {
     cplx<T>* ws = smem_at<cplx<T>>(ws_off);
     if (GEN && pl.dft_n) {
-        if (tw_off != kNoSmem) dense_dft_batch<INV>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));
-        else dense_dft_batch<INV>(ctx, ws, nfft, fstride, pl, tw);
+        // dense transform: on the tensor cores where the kernel has built the fragment table (fp64 solve kernels: tw_off
+        // addresses that table, not a twiddle table), else the scalar version with the twiddles in global memory
+#ifndef BSGP_HOST_EMUL
+        if constexpr (sizeof(T) == 8) {
+            if (tw_off != kNoSmem && pl.n <= 32 && pl.pad_shift == 3 && (nfft & 3) == 0 && (ctx.nt & 31) == 0 && ((nfft >> 2) << (pl.log2n - 3)) <= kDenseTilesPerWarp * (ctx.nt >> 5)) {
+                dense_dft_mma<INV>(ctx, ws, nfft, fstride, pl, (const double*)smem_at<double>(tw_off));
+                return;
+            }
+        }
+#endif
+        dense_dft_batch<INV>(ctx, ws, nfft, fstride, pl, tw);
         return;
     }
     if (tw_off != kNoSmem) run_stages<INV, false>(ctx, ws, nfft, fstride, pl, (const cplx<T>*)smem_at<cplx<T>>(tw_off));

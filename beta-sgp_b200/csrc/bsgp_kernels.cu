@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) bsgp_betadiv_kernel(const double* __restr
     acc[0].clear(); acc[1].clear(); acc[2].clear();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         objective_pixel<double>(dk, x[i], y[i], 0.0, true, acc);
-        if (deriv) deriv[i] = (dk.kind == 1) ? dbeta_pixel<double>(x[i], y[i], beta) : 0.0;
+        if (deriv) deriv[i] = (dk.kind == 1) ? dbeta_pixel<false, double>(x[i], y[i], beta) : 0.0;
     }
     double v[3] = {acc[0].value(), acc[1].value(), acc[2].value()};
     ctx.allreduce_sum(v, 3);
@@ -556,10 +556,15 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     sp.off_ctl = (unsigned)off; off = up128(off + (size_t)(threads / 32) * sp.ctl_stride);
     const size_t tw_bytes = ((size_t)p->nx + (p->ny != p->nx ? p->ny : 0)) * sizeof(cplx<T>);
     sp.tw_smem = tw_bytes <= 16384 ? 1 : 0;             // cluster mode: full tables in shared memory, or global
+    // a dense axis of an fp64 plan keeps the DMMA fragment table of its transform there instead (bsgp_fft.cuh, fill_dense_table)
+    auto tw_bytes_of = [&](int n, int dft_n) -> size_t {
+        if (dft_n && sizeof(T) == 8) return (size_t)8 * n * n;
+        return tw_table_entries(sp.tw_smem, n) * sizeof(cplx<T>);
+    };
     sp.off_twx = (unsigned)off;
     sp.off_twy = (unsigned)off;
-    off = up128(off + tw_table_entries(sp.tw_smem, p->nx) * sizeof(cplx<T>));
-    if (p->ny != p->nx) { sp.off_twy = (unsigned)off; off = up128(off + tw_table_entries(sp.tw_smem, p->ny) * sizeof(cplx<T>)); }
+    off = up128(off + tw_bytes_of(p->nx, p->g.px.dft_n));
+    if (p->ny != p->nx || p->g.py.dft_n != p->g.px.dft_n) { sp.off_twy = (unsigned)off; off = up128(off + tw_bytes_of(p->ny, p->g.py.dft_n)); }
     sp.off_ppx = (unsigned)off; off = up128(off + (size_t)p->nx * sizeof(unsigned short));
     sp.off_ws = (unsigned)off; off = up128(off + p->ws_bytes);
     sp.off_bufs = (unsigned)off;

@@ -157,6 +157,21 @@ BSGP_DEV double mpow(double a, double b) { return pow_inline(a, b); }
 BSGP_DEV float mpow(float a, float b) { return powf(a, b); }
 BSGP_DEV double mlog(double a) { return log(a); }
 BSGP_DEV float mlog(float a) { return logf(a); }
+// The same two functions as ONE shared copy each, for the kernels of small images (DeviceCtxSmall, bsgp_device.cuh): those
+// are bound by instruction fetch, every pixel loop runs once or twice per pass, and an inlined pow() per pixel of every
+// pair and row makes the objective phases the largest functions of an iteration.  CALL is a compile-time property of
+// the execution context, so the large-image kernels keep their call-free loops.
+#ifdef BSGP_HOST_EMUL
+inline double pow_call(double a, double b) { return pow_inline(a, b); }
+inline double log_call(double a) { return log(a); }
+#else
+static __device__ __noinline__ double pow_call(double a, double b) { return pow_inline(a, b); }
+static __device__ __noinline__ double log_call(double a) { return log(a); }
+#endif
+template <bool CALL> BSGP_DEV double mpow_sel(double a, double b) { return CALL ? pow_call(a, b) : pow_inline(a, b); }
+template <bool CALL> BSGP_DEV float mpow_sel(float a, float b) { return powf(a, b); }
+template <bool CALL> BSGP_DEV double mlog_sel(double a) { return CALL ? log_call(a) : log(a); }
+template <bool CALL> BSGP_DEV float mlog_sel(float a) { return logf(a); }
 BSGP_DEV double mexp(double a) { return exp(a); }
 BSGP_DEV float mexp(float a) { return expf(a); }
 BSGP_DEV double mabs(double a) { return fabs(a); }

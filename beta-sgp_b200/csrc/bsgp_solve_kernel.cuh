@@ -4,6 +4,8 @@
 #pragma once
 #include <string.h>
 
+#include <type_traits>
+
 #include "bsgp_device.cuh"
 #include "bsgp_launch.h"
 #include "bsgp_solver.cuh"
@@ -11,7 +13,11 @@
 namespace bsgp {
 
 // shared-memory twiddle table: mode 1 = the full table W_n^k, mode 2 = two-level [W^0 .. W^63][W^(64 m)] (bsgp_fft.cuh)
-template <class Ctx, typename T> __device__ __forceinline__ void fill_twiddles(Ctx& ctx, int mode, int n, const cplx<T>* tw, cplx<T>* dst) {
+template <class Ctx, typename T> __device__ __forceinline__ void fill_twiddles(Ctx& ctx, int mode, int n, const cplx<T>* tw, cplx<T>* dst, int dft_n = 0) {
+    if (dft_n) {          // dense axis: the DMMA fragment table (fp64), nothing otherwise (the scalar version reads global memory)
+        if (sizeof(T) == 8 && mode == 1) fill_dense_table(ctx, n, dft_n, tw, reinterpret_cast<double*>(dst));
+        return;
+    }
     if (mode == 1) {
         for (int k = ctx.tid; k < n; k += ctx.nt) dst[k] = tw[k];
     } else if (mode == 2) {
@@ -22,7 +28,9 @@ template <class Ctx, typename T> __device__ __forceinline__ void fill_twiddles(C
 template <typename T, int NT, int MINB, bool MK>
 __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
     unsigned char* smem = dyn_smem();
-    DeviceCtx ctx = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
+    // 2 CTAs x 256 threads per SM is the configuration of images that are resident in shared memory (bsgp_kernels.cu, plan_setup_t)
+    typename std::conditional<NT == 256 && MINB == 2, DeviceCtxSmall, DeviceCtx>::type ctx;
+    static_cast<DeviceCtx&>(ctx) = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
     ctx.wst = smem + sp.off_ctl + (threadIdx.x >> 5) * sp.ctl_stride;
     ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);
     const int cluster_id = blockIdx.x / a.g.G;
@@ -37,8 +45,8 @@ __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T>
     }
     cplx<T>* twx_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twx);
     cplx<T>* twy_s = reinterpret_cast<cplx<T>*>(smem + sp.off_twy);
-    fill_twiddles(ctx, sp.tw_smem, a.g.nx, a.twx, twx_s);
-    if (sp.off_twy != sp.off_twx) fill_twiddles(ctx, sp.tw_smem, a.g.ny, a.twy, twy_s);
+    fill_twiddles(ctx, sp.tw_smem, a.g.nx, a.twx, twx_s, a.g.px.dft_n);
+    if (sp.off_twy != sp.off_twx) fill_twiddles(ctx, sp.tw_smem, a.g.ny, a.twy, twy_s, a.g.py.dft_n);
     unsigned short* ppx = reinterpret_cast<unsigned short*>(smem + sp.off_ppx);
     fill_pos_table(ctx, a.g.px, ppx);
     if (ctx.tid == 0) {

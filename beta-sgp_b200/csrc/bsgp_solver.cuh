@@ -111,15 +111,15 @@ template <typename T> BSGP_DEV DivK<T> make_divk(int divergence, double beta) {
 // the code of its own kind - the phases that evaluate the objective are the largest functions of the kernel (an inlined
 // pow() per pixel of every pair and row).  The data-only term of the generic beta-divergence, s1 = sum k*gn^beta, changes
 // only when beta does: it has its own small pass (ph_s1) instead of a second pow() in every objective phase.
-template <int KIND, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, T gnv, T den, T xtf_try, KSum* acc) {
+template <int KIND, bool CALL = false, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, T gnv, T den, T xtf_try, KSum* acc) {
     if (KIND == 0) {
         const T ratio = ndiv(gnv, den);
-        acc[0].add((double)nmul(gnv, mlog(ratio)));
+        acc[0].add((double)nmul(gnv, mlog_sel<CALL>(ratio)));
         acc[1].add((double)xtf_try);
         return ratio;
     }
     if (KIND == 1) {
-        const T p1 = mpow(den, dk.bm1);
+        const T p1 = mpow_sel<CALL>(den, dk.bm1);
         acc[1].add((double)nmul(dk.k2, nmul(p1, den)));
         acc[2].add((double)nmul(nmul(dk.k3, gnv), p1));
         return p1;
@@ -127,10 +127,10 @@ template <int KIND, typename T> BSGP_DEV T objective_pixel_k(const DivK<T>& dk, 
     const T ratio = ndiv(gnv, den);
     if (KIND == 2) {
         acc[0].add((double)ratio);
-        acc[1].add((double)mlog(ratio));
+        acc[1].add((double)mlog_sel<CALL>(ratio));
         return ndiv((T)1, den);
     }
-    acc[0].add((double)nmul(gnv, mlog(ratio)));
+    acc[0].add((double)nmul(gnv, mlog_sel<CALL>(ratio)));
     acc[1].add((double)gnv);
     acc[2].add((double)den);
     return (T)1;
@@ -160,9 +160,9 @@ template <typename T> BSGP_DEV double objective_value(const DivK<T>& dk, const d
 }
 
 // per-pixel d D_beta / d beta, sgp.py:495 (term order kept)
-template <typename T> BSGP_DEV T dbeta_pixel(T x, T y, T b) {
+template <bool CALL = false, typename T> BSGP_DEV T dbeta_pixel(T x, T y, T b) {
     const T bm1 = b - (T)1;
-    const T ypb1 = mpow(y, bm1), ypb = nmul(ypb1, y), xpb = mpow(x, b), ly = mlog(y), lx = mlog(x);
+    const T ypb1 = mpow_sel<CALL>(y, bm1), ypb = nmul(ypb1, y), xpb = mpow_sel<CALL>(x, b), ly = mlog_sel<CALL>(y), lx = mlog_sel<CALL>(x);
     const T bm1sq = nmul(bm1, bm1), bbm1 = nmul(b, bm1), bsq = nmul(b, b);
     T s = ndiv(nmul(nmul(-x, ypb1), ly), bm1);
     s = nadd(s, ndiv(nmul(x, ypb1), bm1sq));
@@ -366,7 +366,7 @@ template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_ri_obj0_
     auto one = [&](bool m, T gnv, T bk, T v, T& xt, T& p) {
         if (!m) { xt = (T)0; p = (T)0; return; }
         xt = MK ? ndiv(v, div) : v;
-        p = objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
+        p = objective_pixel_k<KIND, Ctx::kSmall>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In2<T>& in, V2<T> v) {
         V2<T> xt, p;
@@ -528,7 +528,7 @@ template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_ri_trial
         if (!m) { dt = (T)0; p = (T)0; return; }
         dt = MK ? ndiv(v, div) : v;
         const T xt = nadd(xtfv, dt);                       // lam = 1
-        p = objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
+        p = objective_pixel_k<KIND, Ctx::kSmall>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto ca = [&](int i, const In3<T>& in, V2<T> v) {
         V2<T> dt, p;
@@ -551,8 +551,8 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_s1(Ctx ctx, co
     acc.clear();
     auto fetch = [&](int i) { In1<T> r; r.a = ld2(gn, i); return r; };
     auto body = [&](int i, const In1<T>& in) {
-        if (inside<MK>(R, i)) acc.add((double)nmul(k, mpow(in.a.x, b)));
-        if (inside<MK>(R, i + 1)) acc.add((double)nmul(k, mpow(in.a.y, b)));
+        if (inside<MK>(R, i)) acc.add((double)nmul(k, mpow_sel<Ctx::kSmall>(in.a.x, b)));
+        if (inside<MK>(R, i + 1)) acc.add((double)nmul(k, mpow_sel<Ctx::kSmall>(in.a.y, b)));
     };
     pair_loop<1>(ctx, S->nslab, fetch, body);
     return acc.value();
@@ -569,8 +569,8 @@ template <typename T, bool MK, class Ctx> BSGP_NOINLINE double ph_dbeta(Ctx ctx,
         In4<T> r; r.a = ld2(xtf, i); r.b = ld2(dtf, i); r.c = bimg ? ld2(bkgb, i) : mk2(bkg_s, bkg_s); r.d = ld2(gn, i); return r;
     };
     auto body = [&](int i, const In4<T>& in) {
-        if (inside<MK>(R, i)) db += (double)dbeta_pixel(in.d.x, nadd(nadd(in.a.x, nmul(lam, in.b.x)), in.c.x), b);
-        if (inside<MK>(R, i + 1)) db += (double)dbeta_pixel(in.d.y, nadd(nadd(in.a.y, nmul(lam, in.b.y)), in.c.y), b);
+        if (inside<MK>(R, i)) db += (double)dbeta_pixel<Ctx::kSmall>(in.d.x, nadd(nadd(in.a.x, nmul(lam, in.b.x)), in.c.x), b);
+        if (inside<MK>(R, i + 1)) db += (double)dbeta_pixel<Ctx::kSmall>(in.d.y, nadd(nadd(in.a.y, nmul(lam, in.b.y)), in.c.y), b);
     };
     pair_loop<1>(ctx, S->nslab, fetch, body);
     return db;
@@ -590,7 +590,7 @@ template <typename T, bool MK, int KIND, class Ctx> BSGP_NOINLINE R3 ph_trial_k(
     auto one = [&](bool m, T xtfv, T dtfv, T bk, T gnv) -> T {
         if (!m) return (T)0;
         const T xt = nadd(xtfv, nmul(lam, dtfv));
-        return objective_pixel_k<KIND>(dk, gnv, nadd(xt, bk), xt, acc);
+        return objective_pixel_k<KIND, Ctx::kSmall>(dk, gnv, nadd(xt, bk), xt, acc);
     };
     auto body = [&](int i, const In4<T>& in) {
         V2<T> p;

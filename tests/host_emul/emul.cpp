@@ -18,6 +18,7 @@ using namespace bsgp;
 
 struct HostCtx {
     static constexpr bool kFrame = false;
+    static constexpr bool kSmall = false;
     int tid = 0, nt = 1, rank = 0, G = 1, parity = 0;
     void* wst = nullptr;                       // controller state of the one emulated warp
     template <class S> S* ctl() const { return reinterpret_cast<S*>(wst); }

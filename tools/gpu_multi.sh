@@ -4,7 +4,7 @@ N=${1:-2}; tag=${2:-run}
 mkdir -p gpurun_out
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/two_gpu_check.py > gpurun_out/multi_check_${N}_$tag.log 2>&1; echo "check rc=$?"
 tail -3 gpurun_out/multi_check_${N}_$tag.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu_$tag.json 2> gpurun_out/bench_${N}gpu_$tag.err; echo "bench rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 5 --warmup 3 $BENCH_FLAGS > gpurun_out/bench_${N}gpu_$tag.json 2> gpurun_out/bench_${N}gpu_$tag.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench_${N}gpu_$tag.err
 python - <<PY
 import json
