@@ -132,6 +132,45 @@ struct DeviceCtx {
 // of a stamp solve is several times the instruction cache).  kSmall compiles every pass as its plain loop.
 struct DeviceCtxSmall : DeviceCtx {
     static constexpr bool kSmall = true;
+    // Sum all-reduce of EIGHT doubles per thread over the CTA (G = 1), one copy of the code for every call site of the
+    // solver (unused slots carry zeros): the per-K variants of the generic all-reduce add up to a fifth of the
+    // instructions on an iteration's path.  Within the warp the eight values are reduced together by a transposing
+    // butterfly: at distance 16 every lane keeps one half of the values and hands the other half to its partner, at
+    // distance 8 a quarter, at distance 4 one value, then two plain steps - 9 shuffle-adds instead of 40, and the same
+    // pairing (l, l ^ 16), (l, l ^ 8), ... as the generic version, hence the same bits.  Lane l ends with the warp total
+    // of value (l >> 2) & 7; one barrier, then every thread adds the warp partials in warp order.
+    __device__ __forceinline__ void allreduce_sum8(double* v) {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+        const int half = parity & 1;
+        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+        double w[4], u[2], t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double send = b16 ? v[i] : v[i + 4], keep = b16 ? v[i + 4] : v[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double send = b8 ? w[i] : w[i + 2], keep = b8 ? w[i + 2] : w[i];
+            u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const double send = b4 ? u[0] : u[1], keep = b4 ? u[1] : u[0];
+            t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        if ((lane & 3) == 0) sh->warp_part[half][warp][lane >> 2] = t;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sh->warp_part[half][0][j];
+#pragma unroll 1
+        for (int wi = 1; wi < nwarps; ++wi) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += sh->warp_part[half][wi][j];
+        }
+        parity ^= 1;
+    }
 };
 
 // every CTA initialises its two transaction barriers (one arrival each: its own expect_tx); the first

@@ -1078,10 +1078,6 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
     if (batch < 1) return fail(BSGP_E_ARG, "batch must be >= 1");
     if (!in->gn || !in->bkg || !out->x || !out->iters || !out->status || !out->discr || !out->times) return fail(BSGP_E_ARG, "required pointer is NULL");
     CU(cudaSetDevice(p->device));
-    if (p->embedded) {                                             // wrapped plans: plain staging (upload, embed, solve, crop, download)
-        CU(cudaStreamSynchronize((cudaStream_t)stream));
-        return bsgp_solve_batch_host(p, prm, batch, in, out);
-    }
     if (!page_locked(in->gn) || !page_locked(out->x) || !page_locked(in->x0) || !page_locked(in->obj) || (in->bkg_is_image && !page_locked(in->bkg)))
         return fail(BSGP_E_ARG, "bsgp_solve_batch_pinned needs page-locked image buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
     if (in->order) for (int i = 0; i < batch; ++i) if (in->order[i] < 0 || in->order[i] >= batch) return fail(BSGP_E_ARG, "inputs.order is not a permutation of 0..batch-1");
@@ -1089,7 +1085,10 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
     if (const char* e = getenv("BSGP_PIN_MODE")) pin_mode = atoi(e);
     void* x_mapped = nullptr;
     CU(cudaHostGetDevicePointer(&x_mapped, out->x, 0));
-    const size_t img = (size_t)p->ny * p->nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
+    // images in the caller's own shape: a plan whose grid differs from it (sides that are not a power of two) moves them
+    // to and from the grid on the device (solve_t), which needs all of them resident first, like frame mode
+    const size_t img = (size_t)p->img_ny * p->img_nx * p->elem, B = (size_t)batch, tr = (size_t)(prm->maxit + 1);
+    const bool resident_first = p->frame || p->embedded;
     // ---- carve the staging arena
     size_t off = 0;
     auto carve = [&](bool want, size_t bytes) -> size_t { if (!want) return (size_t)-1; const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
@@ -1152,7 +1151,7 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
         return BSGP_OK;
     };
     int rc;
-    if (p->frame) {                                                // the frame kernel has no queue: everything resident first
+    if (resident_first) {                                          // no per-item hand-over: everything resident first
         rc = upload_all(); if (rc) return rc;
         CU(cudaEventRecord(p->ev_copy, sc));
         CU(cudaStreamWaitEvent(sr, p->ev_copy, 0));
@@ -1181,13 +1180,13 @@ int bsgp_solve_batch_pinned(bsgp_plan* p, const bsgp_params* prm, int batch, con
         }
         return BSGP_OK;
     };
-    if (!p->frame) {
+    if (!resident_first) {
         rc = feed();
         if (rc) { cudaGetLastError(); cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
     }
     // ---- run stream: the kernel.  Launched AFTER the copies are queued, so that a launch made synchronous by a tool
     // (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING) cannot wait for flags that nobody has been asked to raise yet.
-    rc = solve_checked(p, prm, batch, &di, &dout, sr, p->ready);
+    rc = solve_checked(p, prm, batch, &di, &dout, sr, resident_first ? nullptr : p->ready);
     if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sr); return rc; }
     // ---- small outputs behind the kernel
     auto down = [&](void* h, size_t o, size_t bytes) -> int { if (h && o != (size_t)-1) CU(cudaMemcpyAsync(h, S + o, bytes, cudaMemcpyDeviceToHost, sr)); return BSGP_OK; };

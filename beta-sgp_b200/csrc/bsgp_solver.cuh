@@ -692,15 +692,32 @@ template <int OP, int K, class Ctx> BSGP_NOINLINE ArOut<K> ar_call(Ctx ctx, ArOu
     io.parity = ctx.parity;
     return io;
 }
+// small-image kernels: every sum of two or more values goes through one eight-wide function (DeviceCtxSmall::allreduce_sum8)
+template <class Ctx> BSGP_NOINLINE ArOut<8> ar_sum8_call(Ctx ctx, ArOut<8> io) {
+    ctx.allreduce_sum8(io.v);
+    io.parity = ctx.parity;
+    return io;
+}
 template <int OP, int K, class Ctx> BSGP_DEV void allreduce_fn(Ctx& ctx, double* v) {
-    ArOut<K> io;
+    if constexpr (Ctx::kSmall && OP == 0 && K > 1) {
+        ArOut<8> io;
 #pragma unroll
-    for (int j = 0; j < K; ++j) io.v[j] = v[j];
-    io.parity = 0;
-    io = ar_call<OP, K>(ctx, io);
+        for (int j = 0; j < 8; ++j) io.v[j] = j < K ? v[j] : 0.0;
+        io.parity = 0;
+        io = ar_sum8_call(ctx, io);
 #pragma unroll
-    for (int j = 0; j < K; ++j) v[j] = io.v[j];
-    ctx.parity = io.parity;
+        for (int j = 0; j < K; ++j) v[j] = io.v[j];
+        ctx.parity = io.parity;
+    } else {
+        ArOut<K> io;
+#pragma unroll
+        for (int j = 0; j < K; ++j) io.v[j] = v[j];
+        io.parity = 0;
+        io = ar_call<OP, K>(ctx, io);
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = io.v[j];
+        ctx.parity = io.parity;
+    }
 }
 
 // The projection root-find of one call (initial projection or one iteration), as a real function: the residual
