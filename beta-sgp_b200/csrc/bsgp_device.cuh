@@ -162,13 +162,13 @@ struct DeviceCtxSmall : DeviceCtx {
         t += __shfl_xor_sync(0xffffffffu, t, 1);
         if ((lane & 3) == 0) sh->warp_part[half][warp][lane >> 2] = t;
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = sh->warp_part[half][0][j];
+        // second stage, per warp: lane j < 8 adds the partials of value j in warp order, eight shuffles hand the totals to
+        // every lane (64 shared-memory loads and adds per thread otherwise)
+        double tot = sh->warp_part[half][0][lane & 7];
 #pragma unroll 1
-        for (int wi = 1; wi < nwarps; ++wi) {
+        for (int wi = 1; wi < nwarps; ++wi) tot += sh->warp_part[half][wi][lane & 7];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += sh->warp_part[half][wi][j];
-        }
+        for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, tot, j);
         parity ^= 1;
     }
 };
