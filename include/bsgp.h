@@ -18,10 +18,11 @@
  *
  * Shapes.  Any ny x nx (the reference's numpy closure accepts any size, sgp.py:108-120; its star-stamp application
  * uses 31 x 31 cut-outs, application_sgp_star_stamps.py:24,58).  Sides that are powers of two in [16, 8192] run on
- * their own FFT grid and need 16-byte aligned image pointers; any other side n <= 4096 runs on a grid of side
- * 2^k >= 2n - 1 ("wrapped plan": linear convolution + fold, exactly the circular operator with the reference's
- * np.fft.fftshift placement, including its one-pixel offset for odd n); the library moves the caller's arrays to and
- * from that grid itself and only needs element alignment.
+ * their own FFT grid and need 16-byte aligned image pointers.  Any other side n <= 32 keeps a grid of 16 or 32 slots and
+ * is transformed by a dense DFT of length n; any other side n <= 4096 runs on a grid of side 2^k >= 2n - 1 ("wrapped":
+ * linear convolution + fold).  Both are exactly the circular operator with the reference's np.fft.fftshift placement,
+ * including its one-pixel offset for odd n; the library moves the caller's arrays to and from the grid itself and only
+ * needs element alignment.
  *
  * Streams.  A plan owns mutable device state (PSF spectra, scratch, the work queue).  Launches on one plan are
  * serialised on the device: every device entry point makes `stream` wait for the plan's previous launch (an event),
