@@ -40,11 +40,12 @@ def _run(bs, name, get_case, **extra):
 # pieces
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(32, 32), (64, 64), (128, 128), (256, 256), (512, 512), (64, 256), (1024, 1024),
-                                   (31, 31), (33, 20), (5, 7), (32, 31), (100, 75), (375, 375), (450, 450)])
+                                   (31, 31), (33, 20), (5, 7), (32, 31), (100, 75), (375, 375), (450, 450),
+                                   (30, 30), (31, 29), (17, 24), (9, 12), (15, 15), (31, 64)])
 def test_psf_operator_matches_numpy(bs, shape):
     """A / A^T closures (sgp.py:108-120): real(ifftn(TF * fftn(x))), TF = fftn(fftshift(psf)).  Sides that are not
-    powers of two (31: application_sgp_star_stamps.py:24; 375 / 450: the paper's sub-frames) run on wrapped plans and
-    must reproduce the odd-size fftshift offset."""
+    powers of two (31: application_sgp_star_stamps.py:24; 375 / 450: the paper's sub-frames) run as dense DFTs (<= 32)
+    or on wrapped grids and must reproduce the odd-size fftshift offset."""
     rng = np.random.default_rng(shape[0] + shape[1])
     n = 5
     x = rng.normal(size=(n,) + shape)
@@ -539,11 +540,13 @@ def test_adaptive_width_configurations_agree(bs, fixtures, golden):
             assert np.abs(a_ - b_).max() <= 1e-9 * np.abs(a_).max()
 
 
-@pytest.mark.parametrize("shape", [(64, 256), (128, 32)])
+@pytest.mark.parametrize("shape", [(64, 256), (128, 32), (31, 29), (30, 30), (15, 13), (24, 31), (33, 20)])
 def test_non_square_images_against_oracle(bs, shape):
-    """Rectangular power-of-two images (row and column transforms of different length, uneven cluster split):
-    KL with a uint8 scalar background as loadmat delivers it (simulation_test_sgp.py:22) and beta-SGP with the
-    flux projection and a 2-D background."""
+    """Rectangular images (row and column transforms of different length, uneven cluster split): KL with a uint8 scalar
+    background as loadmat delivers it (simulation_test_sgp.py:22) and beta-SGP with the flux projection and a 2-D
+    background.  Powers of two, and sides that are not: dense axes of different length on the same 32-slot grid (31 x 29:
+    two tensor-core tables), an even dense length with its Nyquist column (30), the 16-slot grid (15 x 13) and a wrapped
+    axis next to a dense one (33 x 20), all through the masked small-image kernel."""
     from oracle import sgp_oracle as orc
     ny, nx = shape
     rng = np.random.default_rng(ny + nx)
