@@ -381,6 +381,7 @@ struct bsgp_plan {
     int num_sms = 0, max_smem = 0, smem_per_sm = 0;
     int want_G = 0, want_threads = 0;
     bool configured = false;
+    bool small_try = true;       // automatic configuration of small slabs: try 3 CTAs x 128 threads first (plan_setup_t)
     ConvGeom g{};
     size_t ws_bytes = 0, smem_bytes = 0, conv_smem = 0, elem = 8;
     SmemPlan sp{};
@@ -527,7 +528,7 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     const size_t nslab = npix / G;
     const bool small_slab = nslab * sizeof(T) <= 16384;
     int threads = p->want_threads;
-    if (threads <= 0) threads = small_slab ? 256 : 128;
+    if (threads <= 0) threads = small_slab ? (p->small_try ? 128 : 256) : 128;
     if (threads != 256 && threads != 512 && threads != 128) return fail(BSGP_E_ARG, "threads must be 128, 256 or 512");
     int minb = threads >= 512 ? 1 : (threads >= 256 ? (small_slab ? 2 : 1) : (small_slab ? 3 : 4));
     if (const char* e = getenv("BSGP_MINB")) {             // tuning experiments: CTAs per SM
@@ -582,6 +583,13 @@ template <typename T> static int plan_setup_t(bsgp_plan* p) {
     int mask = 0;
     for (int k = 0; k < NBUF; ++k) {
         if (used + slab_bytes <= budget) { mask |= 1 << kResidencyOrder[k]; used += slab_bytes; }
+    }
+    // Small slabs, automatic configuration: three 128-thread CTAs per SM if everything but the background image stays
+    // resident in a third of the SM's shared memory (32 x 32 fp64 stamps: 8192 stamps 19.7 ms against 22.8 ms for two
+    // 256-thread CTAs); otherwise (e.g. 31 x 31 cut-outs, whose tensor-core table takes 8 KB) two 256-thread CTAs.
+    if (p->small_try && small_slab && p->want_threads <= 0 && (mask | (1 << B_BKG)) != (1 << NBUF) - 1) {
+        p->small_try = false;
+        return plan_setup_t<T>(p);
     }
     p->resident_mask = mask;
     p->smem_bytes = used;
@@ -885,6 +893,7 @@ int bsgp_plan_configure(bsgp_plan* p, int cluster_size, int threads) {
     plan_free_buffers(p);
     p->configured = false;
     p->want_G = cluster_size; p->want_threads = threads;
+    p->small_try = true;
     return plan_setup(p);
 }
 

@@ -28,8 +28,9 @@ template <class Ctx, typename T> __device__ __forceinline__ void fill_twiddles(C
 template <typename T, int NT, int MINB, bool MK>
 __global__ void __launch_bounds__(NT, MINB) bsgp_solve_kernel(const SolveArgs<T> a, const SmemPlan sp, const size_t tf_stride) {
     unsigned char* smem = dyn_smem();
-    // 2 CTAs x 256 threads per SM is the configuration of images that are resident in shared memory (bsgp_kernels.cu, plan_setup_t)
-    typename std::conditional<NT == 256 && MINB == 2, DeviceCtxSmall, DeviceCtx>::type ctx;
+    // 2 CTAs x 256 threads and 3 CTAs x 128 threads per SM are the configurations of images that are resident in shared memory
+    // (bsgp_kernels.cu, plan_setup_t)
+    typename std::conditional<(NT == 256 && MINB == 2) || (NT == 128 && MINB == 3), DeviceCtxSmall, DeviceCtx>::type ctx;
     static_cast<DeviceCtx&>(ctx) = make_ctx(reinterpret_cast<SharedCtl*>(smem), a.g.G);
     ctx.wst = smem + sp.off_ctl + (threadIdx.x >> 5) * sp.ctl_stride;
     ImgState<T>* S = reinterpret_cast<ImgState<T>*>(smem + sp.off_state);

@@ -1,10 +1,13 @@
 #!/bin/bash
-run() { python bench.py --no-extra --no-cpu-baseline --no-clocks --steps 3 --workload stamps32 "$@" 2>/dev/null | grep "^{" | python -c "
+# stamp / cut-out workloads under other CTA configurations; logged to gpurun_out/stamps_cfg.log
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/stamps_cfg.log) 2>&1
+run() { python bench.py --no-extra --no-cpu-baseline --no-clocks --steps 3 "$@" 2>gpurun_out/stamps_cfg_err.log | grep "^{" | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('kernel_ms', round(d['roofline']['kernel_ms'],3), 'value', round(d['value'],1), 'cfg', d['config']['cluster_size'], d['config']['threads'], d['config']['clusters_in_flight'], d['config']['smem_bytes'])
-"; }
-echo "default:"; run
-echo "128 thr (minb 3):"; run --threads 128
-echo "128 thr minb 4:"; BSGP_MINB=4 run --threads 128
-echo "256 thr minb 1:"; BSGP_MINB=1 run --threads 256
+" || tail -3 gpurun_out/stamps_cfg_err.log; }
+for w in stamps32 cutouts31; do
+echo "$w default:"; run --workload $w
+echo "$w 128 thr (3 CTAs/SM):"; run --workload $w --threads 128
+done
