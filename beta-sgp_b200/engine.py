@@ -133,10 +133,13 @@ def get_plan(ny, nx, dtype="float64", device=0, cluster_size=0, threads=0):
 
 # Width of the CTA configuration as a function of the number of images a GPU holds (measured on B200, 256 x 256 beta-SGP,
 # tools/latency_probe.py): the default (clusters of 8 CTAs x 128 threads, 4 CTAs of different images per SM, 71 images in
-# flight) has the best throughput but 200 us per iteration of ONE image; 16 x 128 reaches 118 us and 8 x 256 112 us with
-# 31 / 15 images in flight, 16 x 256 74 us with 7.  A GPU that holds fewer images than slots is bounded by its longest solve,
-# so it trades slots for latency.  (threshold on images per default slot, (cluster_size, threads)); first match wins.
-_WIDTH_RULES = ((1.7, (0, 0)), (0.7, (16, 128)), (0.11, (0, 256)), (0.0, (16, 256)))
+# flight) has the best throughput but 200 us per iteration of ONE image; 16 x 128 reaches 118 us with 31 images in flight,
+# 8 x 256 112 us with 15, 16 x 256 74 us with 7.  A GPU that holds fewer images than slots is bounded by its longest solve,
+# so it trades slots for latency.  Thresholds from tools/width_probe.py (one GPU plays every rank of a world of W on the
+# 320-tile field; slowest rank in ms for default / 16 x 128 / 8 x 256 / 16 x 256): 160 images per rank 38.8 / 42.7 / 54.7 /
+# 73.6; 80: 28.8 / 24.5 / 28.8 / 38.0; 40: 23.3 / 16.2 / 17.7 / 20.8; 20: 20.4 / 13.1 / 13.1 / 11.6; 10: 19.8 / 11.8 / 13.0 /
+# 8.4.  8 x 256 never wins.  (threshold on images per default slot, (cluster_size, threads)); first match wins.
+_WIDTH_RULES = ((1.7, (0, 0)), (0.42, (16, 128)), (0.0, (16, 256)))
 
 
 def auto_config(ny, nx, batch, dtype="float64"):

@@ -521,7 +521,7 @@ def test_adaptive_width_configurations_agree(bs, fixtures, golden):
     configuration it can select must give bit-identical results (same reduction order per image is NOT guaranteed across
     cluster sizes, so: identical iteration counts, image <= 1e-9)."""
     assert bs.engine.auto_config(256, 256, 320) == (0, 0) and bs.engine.auto_config(256, 256, 80) == (16, 128)
-    assert bs.engine.auto_config(256, 256, 40) == (0, 256) and bs.engine.auto_config(256, 256, 1) == (16, 256)
+    assert bs.engine.auto_config(256, 256, 40) == (16, 128) and bs.engine.auto_config(256, 256, 20) == (16, 256) and bs.engine.auto_config(256, 256, 1) == (16, 256)
     assert bs.engine.auto_config(32, 32, 5) == (0, 0) and bs.engine.auto_config(31, 31, 5) == (0, 0) and bs.engine.auto_config(8192, 8192, 1) == (0, 0)
     names = ["tile00", "tile01", "tile07"]
     ref = None
