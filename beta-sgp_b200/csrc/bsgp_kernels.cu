@@ -243,9 +243,11 @@ __global__ void bsgp_assemble_tiles_kernel(const T* __restrict__ tiles, const in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wrapped plans: image sides that are not a power of two in [16, 8192] (the reference's numpy closure takes any
+// Embedded plans: image sides that are not a power of two in [16, 8192] (the reference's numpy closure takes any
 // size, sgp.py:108-120; its star-stamp application runs it on 31 x 31 cut-outs, application_sgp_star_stamps.py:24,58).
-// The image sits at the origin of a power-of-two grid of side P >= 2 n - 1 (zeros elsewhere) and the circular
+// Per axis (bsgp_wrap.h): a side n <= 32 keeps a grid of 16 or 32 slots and is transformed by a dense DFT of length n
+// over the first n slots (the circular operator itself, no fold); any other side is WRAPPED:
+// the image sits at the origin of a power-of-two grid of side P >= 2 n - 1 (zeros elsewhere) and the circular
 // convolution with h = fftshift(psf) (sgp.py:109: np.roll by n // 2, which for odd n puts the PSF centre at index
 // n - 1, not 0) is computed as the LINEAR convolution on the grid followed by the fold out[i] = z[i] + z[i + n]
 // (conv_cols / conv_rows_inverse).  A^T = correlation with h = convolution with h~[j] = h[(-j) mod n], so both

@@ -147,7 +147,7 @@ def auto_config(ny, nx, batch, dtype="float64"):
     npix = int(ny) * int(nx)
     pow2 = all(v >= 16 and v & (v - 1) == 0 for v in (int(ny), int(nx)))
     if not pow2 or npix * (8 if dtype == "float64" else 4) <= 64 * 1024 or npix >= (1 << 20):
-        return (0, 0)                                   # stamps (one CTA each), wrapped plans and frame mode: one configuration
+        return (0, 0)                                   # stamps (one CTA each), embedded (dense / wrapped) plans and frame mode: one configuration
     slots = 71.0                                        # images in flight of the default configuration on 148 SMs
     for thr, cfg in _WIDTH_RULES:
         if batch >= thr * slots:

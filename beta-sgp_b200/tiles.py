@@ -95,7 +95,7 @@ def reconstruct_full_image_from_patches(tiles, origins, shape, feather=None, dev
 
 def restore_frame(frame, psf, bkg, subdiv_shape=(256, 256), overlap=0, betaParam=1.005, divergence="beta", feather=None, device=0,
                   on_failure="raise", **kw):
-    """Frame in, frame out: tiles of `subdiv_shape` (powers of two for the circular operator) are cut on the device, restored
+    """Frame in, frame out: tiles of `subdiv_shape` (any shape; powers of two run on their own FFT grid) are cut on the device, restored
     in one persistent-kernel launch (each tile conserves its own flux sum(gn - bkg), the solver's default, sgp.py:661-666)
     and cross-faded back.  `bkg` is a scalar or a background map of the frame's shape; `psf` has the tile's shape.
     Returns (restored frame as a CUDA tensor, BatchResult of the tiles, origins)."""
