@@ -297,29 +297,31 @@ template <class Ctx, typename T> BSGP_DEV void fill_dense_table(Ctx& ctx, int ng
 // Preconditions (checked by fft_batch): grid side pl.n = 16 or 32 with padding period 8 (pad_shift 3), nfft a multiple of 4,
 // whole warps, at most kDenseTilesPerWarp tiles per warp.  The step loop is unrolled over the grid's 8 (or 4) steps so that
 // every address is base + immediate: fpad(4 s + jl) = 4 s + jl + (s >> 1) for a padding period of 8.
-template <bool INV, class Ctx>
+// FAST (compile time): the transform fills the grid's last step (n > grid - 4: the 31-point case) and the tiles divide evenly
+// among the warps, TPW each: no step or tile predicates, only the last step's A operand is guarded.
+template <bool INV, int TPW, bool FAST, class Ctx>
 BSGP_DEV void dense_dft_mma(Ctx& ctx, cplx<double>* ws, int nfft, int fstride, const FftPlan& pl, const double* tab) {
     const int n = pl.dft_n;
     const int lane = ctx.tid & 31, warp = ctx.tid >> 5, nwarps = ctx.nt >> 5;
     const int per = (n >> 1) + 1;
     const int lgNT = pl.log2n - 3, tiles = (nfft >> 2) << lgNT;          // 8 x 8 tiles: 4 frequencies (cos, sin) x 4 transforms (re, im); all of the table's column tiles
-    const int S = (n + 3) >> 2, Sfull = pl.n >> 2;
+    const int S = FAST ? 8 : (n + 3) >> 2, Sfull = FAST ? 8 : pl.n >> 2;
     double* wsd = reinterpret_cast<double*>(ws);
     const int part = (lane >> 2) & 1, jl = lane & 3;
-    double c0[kDenseTilesPerWarp], c1[kDenseTilesPerWarp];
+    double c0[TPW], c1[TPW];
 #pragma unroll
-    for (int i = 0; i < kDenseTilesPerWarp; ++i) {
+    for (int i = 0; i < TPW; ++i) {
         c0[i] = 0.0; c1[i] = 0.0;
         const int tile = warp + i * nwarps;                   // tile = nt + NT * mt
-        if (tile < tiles) {
+        if (FAST || tile < tiles) {
             const int mt = tile >> lgNT, nt = tile & ((1 << lgNT) - 1);
             const double* arow = wsd + 2 * ((4 * mt + (lane >> 3)) * fstride + jl) + part;
             const double* brow = tab + (nt * Sfull) * 32 + lane;
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                if (s < S) {
+                if (FAST || s < S) {
                     double a = arow[2 * (4 * s + (s >> 1))];
-                    a = (4 * s + jl < n) ? a : 0.0;           // a slot beyond the transform may hold anything
+                    if (!FAST || s == 7) a = (4 * s + jl < n) ? a : 0.0;           // a slot beyond the transform may hold anything
                     const double b = brow[s * 32];
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                                  : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
@@ -329,9 +331,9 @@ BSGP_DEV void dense_dft_mma(Ctx& ctx, cplx<double>* ws, int nfft, int fstride, c
     }
     ctx.sync();                                               // every warp has read its inputs
 #pragma unroll
-    for (int i = 0; i < kDenseTilesPerWarp; ++i) {
+    for (int i = 0; i < TPW; ++i) {
         const int tile = warp + i * nwarps;
-        if (tile < tiles) {                                   // warp-uniform
+        if (FAST || tile < tiles) {                           // warp-uniform
             const int mt = tile >> lgNT, nt = tile & ((1 << lgNT) - 1);
             const double other = __shfl_xor_sync(0xffffffffu, c1[i], 4);     // the S sum of the other part
             const double lo = part ? c0[i] - other : c0[i] + other;
@@ -363,7 +365,12 @@ BSGP_NOINLINE void fft_batch(Ctx ctx, unsigned ws_off, int nfft, int fstride, co
 #ifndef BSGP_HOST_EMUL
         if constexpr (sizeof(T) == 8) {
             if (tw_off != kNoSmem && pl.n <= 32 && pl.pad_shift == 3 && (nfft & 3) == 0 && (ctx.nt & 31) == 0 && ((nfft >> 2) << (pl.log2n - 3)) <= kDenseTilesPerWarp * (ctx.nt >> 5)) {
-                dense_dft_mma<INV>(ctx, ws, nfft, fstride, pl, (const double*)smem_at<double>(tw_off));
+                const double* tab = (const double*)smem_at<double>(tw_off);
+                const int tiles = (nfft >> 2) << (pl.log2n - 3), nwarps = ctx.nt >> 5;
+                const bool full = pl.n == 32 && pl.dft_n > 28;
+                if (full && tiles == 2 * nwarps) dense_dft_mma<INV, 2, true>(ctx, ws, nfft, fstride, pl, tab);
+                else if (full && tiles == 4 * nwarps) dense_dft_mma<INV, 4, true>(ctx, ws, nfft, fstride, pl, tab);
+                else dense_dft_mma<INV, kDenseTilesPerWarp, false>(ctx, ws, nfft, fstride, pl, tab);
                 return;
             }
         }
