@@ -125,6 +125,10 @@ def _solve_one(divergence, gn, psf, bkg, kw, flux, betaParam, obj, save, use_ori
     status = int(res.status[0])
     if status != _capi.ST_OK:
         raise _status_error(status)
+    if isinstance(flux, np.ndarray) and flux.dtype.kind == "f":
+        # `flux /= scaling` (sgp.py:211 / 666) is an in-place division when the caller hands over an ndarray (the 0-d result
+        # of np.sum is one): the caller's array holds the scaled flux afterwards.  Reproduced; numpy scalars are rebound.
+        flux /= res.scalars[0, 0]
     iters = int(res.iters[0])
     _write_log(res, kw, float(res.scalars[0, 4]))
     err = None

@@ -257,6 +257,14 @@ def test_dropin_entry_points(bs, get_case, golden, tmp_path, monkeypatch, capsys
         bs.sgp(gn, psf, bkg, MAXIT=2, errflag=True)
     with pytest.raises(ValueError):                                       # non-positive flux, proj_type 1
         bs.sgp_betaDiv(gn, psf, np.float64(1e9), proj_type=1, MAXIT=3)
+    # `flux /= scaling` (sgp.py:211 / 666): an ndarray flux (the 0-d result of np.sum, or an element view) is scaled in place
+    # in the caller's memory; a numpy scalar is only rebound
+    f0 = float((gn - bkg).sum())
+    flux_arr = np.array(f0)
+    flux_scalar = np.float64(f0)
+    bs.sgp_betaDiv(gn, psf, bkg, proj_type=1, MAXIT=2, flux=flux_arr, verbose=False)
+    bs.sgp_betaDiv(gn, psf, bkg, proj_type=1, MAXIT=2, flux=flux_scalar, verbose=False)
+    assert float(flux_arr) == f0 / float(gn.max()) and float(flux_scalar) == f0
 
 
 def test_errflag_trace(bs, fixtures):
