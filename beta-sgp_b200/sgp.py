@@ -111,6 +111,9 @@ def _solve_one(divergence, gn, psf, bkg, kw, flux, betaParam, obj, save, use_ori
     if kw["init_recon"] == 1:                                                                  # sgp.py:168-170
         np.random.seed(42)
         x0 = np.random.randn(*gn.shape)[None]
+    if not hasattr(bkg, "flatten"):
+        # the reference calls bkg.flatten() (sgp.py:182 / 636): a Python float or int background fails there
+        raise AttributeError(f"'{type(bkg).__name__}' object has no attribute 'flatten'")
     bkg_a = np.asarray(bkg, dtype=np.float64)
     if bkg_a.size == gn.size:
         bkg_a = bkg_a.reshape((1,) + gn.shape)

@@ -257,6 +257,8 @@ def test_dropin_entry_points(bs, get_case, golden, tmp_path, monkeypatch, capsys
         bs.sgp(gn, psf, bkg, MAXIT=2, errflag=True)
     with pytest.raises(ValueError):                                       # non-positive flux, proj_type 1
         bs.sgp_betaDiv(gn, psf, np.float64(1e9), proj_type=1, MAXIT=3)
+    with pytest.raises(AttributeError, match="flatten"):                  # bkg.flatten() of a Python float (sgp.py:182)
+        bs.sgp(gn, psf, 10.0, MAXIT=2)
     # `flux /= scaling` (sgp.py:211 / 666): an ndarray flux (the 0-d result of np.sum, or an element view) is scaled in place
     # in the caller's memory; a numpy scalar is only rebound
     f0 = float((gn - bkg).sum())
